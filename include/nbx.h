@@ -1,0 +1,146 @@
+/* nbx.h — C ABI of the B200-native N-body force engine (libnbx.so).
+ *
+ * Drop-in boundary for the ONE data-parallel hot path of UoB-HPC/stdpar-nbody: the per-step
+ * force + leapfrog pipeline behind `sim_func_t<T,N>` (reference src/main.cpp:16-17,58-64).
+ * Plain pointers and sizes only; no C++/torch types. Every entry point names the reference
+ * interface it replaces (paths relative to the reference root).
+ *
+ * State layout at the boundary is EXACTLY System<T,N>::state_t (src/system.h:41-50):
+ *   m  : T[n]              x, v, a, ao : vec<T,N>[n]  (packed AoS, N*sizeof(T) stride)
+ * T = float (precision NBX_F32) or double (NBX_F64); N = dim in {2,3}.
+ * Internally the engine keeps (x,y,z,m)-packed 16/32-byte records in HBM.
+ *
+ * Threading: one caller thread per engine; every call returns after its work is enqueued on the engine's
+ * CUDA stream, calls that copy to host memory return after the copy has completed. nbx_sync() blocks.
+ * Errors: every function returns NBX_OK (0) or a negative code; nbx_last_error() gives the message of the
+ * last failure on the calling thread. There is NO CPU fallback: without a CUDA device nbx_create fails.
+ */
+#ifndef NBX_H
+#define NBX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NBX_VERSION 100
+
+enum nbx_status {
+  NBX_OK              = 0,
+  NBX_ERR_INVALID     = -1, /* bad argument / unsupported combination                                  */
+  NBX_ERR_CUDA        = -2, /* a CUDA runtime call failed (message has the CUDA error string)           */
+  NBX_ERR_NO_DEVICE   = -3, /* no usable CUDA device: the product has no CPU path                       */
+  NBX_ERR_CAPACITY    = -4, /* octree deeper than the supported key depth / node capacity exceeded      */
+  NBX_ERR_COMM        = -5, /* NCCL failure or communicator not initialised                             */
+  NBX_ERR_STATE       = -6  /* call order violated (e.g. compute_force before build_tree)               */
+};
+
+/* src/arguments.h:16-21 SimulationAlgo (same order) */
+enum nbx_algorithm { NBX_ALL_PAIRS = 0, NBX_ALL_PAIRS_COLLAPSED = 1, NBX_OCTREE = 2, NBX_BVH = 3 };
+/* sizeof(T) */
+enum nbx_precision { NBX_F32 = 4, NBX_F64 = 8 };
+
+typedef struct nbx_engine nbx_engine;
+
+typedef struct nbx_config {
+  uint32_t struct_size;  /* = sizeof(nbx_config)                                                          */
+  int32_t  dim;          /* -DDIM_SIZE (src/main.cpp:5-7): 2 or 3                                         */
+  int32_t  precision;    /* --precision (src/arguments.h:58-69): NBX_F32 | NBX_F64                        */
+  int32_t  algorithm;    /* --algorithm (src/arguments.h:70-86)                                           */
+  uint32_t n;            /* System::size (src/system.h:14)                                                */
+  int32_t  device;       /* CUDA device ordinal                                                           */
+  double   dt;           /* System::dt   (src/system.h:16)                                                */
+  double   G;            /* System::constant (src/system.h:17)                                            */
+  double   theta;        /* --theta (src/arguments.h:31)                                                  */
+  /* multi-GPU: this engine computes forces for / integrates targets [rank*ceil(n/world), ...) and all-gathers
+   * positions each step; world_size 1 = single GPU. */
+  int32_t  rank;
+  int32_t  world_size;
+  uint32_t flags;        /* NBX_FLAG_* */
+  uint32_t reserved;
+} nbx_config;
+
+#define NBX_FLAG_COLLAPSED_FIX_Z 0x1u /* non-default deviation: also accumulate z in all-pairs-collapsed */
+#define NBX_FLAG_NO_FUSED_INTEGRATE 0x2u /* nbx_step runs force and leapfrog as separate kernels */
+
+const char* nbx_last_error(void);
+int nbx_version(void);
+/* number of CUDA devices visible (0 on a box without a GPU) */
+int nbx_device_count(void);
+
+/* replaces: System<T,N> construction + tree alloc (src/system.h:27-36, src/octree.h:42-51, src/bvh.h:147-164) */
+int nbx_create(const nbx_config* cfg, nbx_engine** out);
+/* replaces: ~System / bvh::dealloc (src/bvh.h:167-172) */
+int nbx_destroy(nbx_engine* e);
+
+/* replaces: System::state() pointer hand-off (src/system.h:47-50). Host arrays in state_t layout. Any pointer
+ * may be NULL to skip that array. */
+int nbx_upload(nbx_engine* e, const void* m, const void* x, const void* v, const void* a, const void* ao);
+int nbx_download(nbx_engine* e, void* m, void* x, void* v, void* a, void* ao);
+
+/* replaces: the `kernels()` lambda of run_all_pairs / run_octree / run_bvh (src/all_pairs.h:86-92,
+ * src/octree.h:321-328, src/bvh.h:382-397): `steps` x (force + accelerate_step), device resident. */
+int nbx_step(nbx_engine* e, uint32_t steps);
+/* same, bracketed by CUDA events on the engine stream; *ms = device time of the `steps` steps */
+int nbx_step_timed(nbx_engine* e, uint32_t steps, float* ms);
+int nbx_sync(nbx_engine* e);
+
+/* ---- per-phase entry points (the finer seams used inside the reference drivers) ---------------------------- */
+/* all_pairs_force(System&)            src/all_pairs.h:14-27  */
+int nbx_all_pairs_force(nbx_engine* e);
+/* all_pairs_collapsed_force(System&)  src/all_pairs.h:29-50  */
+int nbx_all_pairs_collapsed_force(nbx_engine* e);
+/* System::accelerate_step()           src/system.h:52-60     */
+int nbx_accelerate_step(nbx_engine* e);
+/* System::calc_energies()             src/system.h:62-79  -> T kinetic, T gravitational (as double) */
+int nbx_calc_energies(nbx_engine* e, double* kinetic, double* gravitational);
+
+/* bounding_box(span)                  src/bvh.h:17-22   xmin/xmax: T[dim] host */
+int nbx_bvh_bounding_box(nbx_engine* e, void* xmin, void* xmax);
+/* hilbert_sort(System&, aabb)         src/bvh.h:25-96   (uses the box of the last nbx_bvh_bounding_box) */
+int nbx_bvh_hilbert_sort(nbx_engine* e);
+/* bvh::build_tree(System&)            src/bvh.h:175-244 */
+int nbx_bvh_build_tree(nbx_engine* e);
+/* bvh::compute_force(System&, theta)  src/bvh.h:251-324 */
+int nbx_bvh_compute_force(nbx_engine* e);
+/* artefacts of the last hilbert_sort: keys[n] BEFORE sorting (body order at entry), perm[n] (new[i]=old[perm[i]]) */
+int nbx_bvh_get_keys(nbx_engine* e, uint64_t* keys, uint32_t* perm);
+/* bvh::m / bw / b arrays (src/bvh.h:103-106): node_m T[nn*(dim+1)], bw T[nn], b T[nn*2*dim]; nn = *nnodes */
+int nbx_bvh_get_nodes(nbx_engine* e, uint64_t* nnodes, void* node_m, void* bw, void* b);
+
+/* octree::clear + compute_bounds + insert + compute_tree  src/octree.h:77-224 */
+int nbx_octree_build(nbx_engine* e);
+/* octree::compute_force(System&, theta)                   src/octree.h:258-263 */
+int nbx_octree_compute_force(nbx_engine* e);
+/* root cube of the last build (src/octree.h:93-112): side T, root_x T[dim]; nodes = 1 + 2^dim * internal cells
+ * (what next_free_child_group would read, src/octree.h:152) */
+int nbx_octree_get_root(nbx_engine* e, void* side, void* root_x, uint64_t* nodes_used);
+/* numbering-independent canonical form of the last build, DFS child order, one record per NON-EMPTY node:
+ * depth u32, path u64 (dim bits per level, root first), kind u32 (1 body leaf / 0 internal), monopole T[dim+1]
+ * (x.., mass). Pass NULL arrays to query *count only. */
+int nbx_octree_get_canonical(nbx_engine* e, uint64_t* count, uint32_t* depth, uint64_t* path, uint32_t* kind,
+                             void* monopole);
+
+/* ---- multi-GPU plumbing (one process per GPU; rendezvous is the caller's, e.g. torch.distributed) ---------- */
+#define NBX_UNIQUE_ID_BYTES 128
+int nbx_comm_unique_id(void* id128);
+int nbx_comm_init_rank(nbx_engine* e, const void* id128);
+
+/* ---- measurement helpers ---------------------------------------------------------------------------------- */
+/* FMA-pipe peak microbenchmark on the engine's device: precision NBX_F32 -> FFMA, NBX_F64 -> DFMA.
+ * *tflops = 2 * fma/s / 1e12 measured with CUDA events. */
+int nbx_measure_fma_peak(int device, int precision, double* tflops);
+/* counters of the engine since creation: kernels launched by this library, bytes copied H2D / D2H */
+int nbx_get_counters(nbx_engine* e, uint64_t* kernel_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+/* per-phase device time (ms) of the last nbx_step* call's LAST step, in the reference's CSV column order:
+ * all-pairs: force, accel; bvh: bbox, sort, multipoles, force approx, accel; octree: clear+bbox(bounds),
+ * insert(build), multipoles, force approx, accel. Needs nbx_set_phase_timing(e,1). */
+int nbx_set_phase_timing(nbx_engine* e, int enable);
+int nbx_get_phase_ms(nbx_engine* e, float* ms, int capacity, int* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBX_H */

@@ -1,0 +1,637 @@
+// nbx_allpairs.cu — O(n^2) force kernels + leapfrog for sm_100a.
+//
+//   all_pairs_kernel      : reference all_pairs_force            (src/all_pairs.h:14-27)   [K1]
+//   collapsed_kernel      : reference all_pairs_collapsed_force  (src/all_pairs.h:29-50)   [K2]
+//   accelerate_kernel     : reference System::accelerate_step    (src/system.h:52-60)      [K3]
+//   energy kernels        : reference System::calc_energies      (src/system.h:62-79)      [K4]
+//
+// Design: targets are register-blocked (TI per thread), the j bodies stream through
+// shared memory in TILE-sized chunks staged by 1-D TMA bulk copies (cp.async.bulk + mbarrier, STAGES deep) and
+// are read back as broadcast LDS.128. The pair interaction is FMA/SFU work only: the kernel is bound by the
+// MUFU pipe (sqrt + rcp per pair), tensor cores are deliberately not used. The j range is split over gridDim.y
+// so that the grid has >= ~32 waves of CTAs; partial sums are combined in a FIXED order by the last-arriving CTA
+// of each target block, which also applies the leapfrog update (fused epilogue, double-buffered positions).
+#include <cfloat>
+#include <cstdio>
+
+#include "nbx_internal.cuh"
+
+namespace nbx {
+
+// ---- math -----------------------------------------------------------------------------------------------------
+// 1 / (d2^1.5 + eps)   (vec.h:249-252 dist3; eps = numeric_limits<T>::epsilon()).  d2 == 0 gives 1/eps (finite), so a
+// self pair contributes m * 0 * (1/eps) = 0 exactly as `m*(pj-pi)/dist3` does in the reference, without a branch.
+__device__ __forceinline__ float inv_dist3(float d2) {
+  float sq, inv;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(d2));          // MUFU.SQRT
+  float den = fmaf(d2, sq, FLT_EPSILON);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(den));         // MUFU.RCP
+  return inv;
+}
+__device__ __forceinline__ double inv_dist3(double d2) {
+  // rsqrt seed (MUFU.RSQ64H) refined on the FP64 pipe: one cubic step on y, then a Heron correction on sqrt.
+  double d2c = fmax(d2, 1e-300);
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d2c));
+  double t = d2c * y;
+  double e = fma(-t, y, 1.0);
+  double q = e * fma(0.375, e, 0.5);
+  y        = fma(y, q, y);
+  double sq = d2 * y;                       // d2 == 0 -> 0
+  double r  = fma(-sq, sq, d2);
+  sq        = fma(r, 0.5 * y, sq);
+  double den = fma(d2, sq, DBL_EPSILON);
+  double inv;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(inv) : "d"(den));        // MUFU.RCP64H
+  double e1 = fma(-den, inv, 1.0);
+  inv       = fma(inv, fma(e1, e1, e1), inv);
+  double e2 = fma(-den, inv, 1.0);
+  inv       = fma(inv, e2, inv);
+  return inv;
+}
+
+// round-to-nearest ops that the compiler may not contract: the leapfrog restates system.h:56-58 operation by
+// operation so that, given the same `a`, it is bit-identical to the pinned (-ffp-contract=off) reference.
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+
+// ---- TMA bulk copy + mbarrier helpers (PTX) -------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// 1-D bulk async copy global -> shared, completion signalled on `bar` (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// L2-only (cache-global) vec4 accesses for data produced by other CTAs of the same launch
+__device__ __forceinline__ float4 ldcg_v4(const float4* p) { return __ldcg(p); }
+__device__ __forceinline__ double4 ldcg_v4(const double4* p) {
+  double2 lo = __ldcg(reinterpret_cast<const double2*>(p));
+  double2 hi = __ldcg(reinterpret_cast<const double2*>(p) + 1);
+  return make_double4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ void stcg_v4(float4* p, float4 v) { __stcg(p, v); }
+__device__ __forceinline__ void stcg_v4(double4* p, double4 v) {
+  __stcg(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
+  __stcg(reinterpret_cast<double2*>(p) + 1, make_double2(v.z, v.w));
+}
+
+// ---- leapfrog (system.h:52-60) --------------------------------------------------------------------------------
+template <typename T>
+struct LeapArgs {
+  const vec4_t<T>* xm_in;
+  vec4_t<T>* xm_out;
+  vec4_t<T>* v;
+  vec4_t<T>* a;
+  vec4_t<T>* ao;
+  T dt;
+};
+
+// x += dt*v + 0.5*dt*dt*ao ; v += 0.5*dt*(a+ao) ; ao = a     (all vec ops componentwise, same association)
+template <typename T, int D>
+__device__ __forceinline__ void leapfrog_body(const LeapArgs<T>& p, uint32_t i, vec4_t<T> anew) {
+  vec4_t<T> xm = p.xm_in[i];
+  vec4_t<T> v  = p.v[i];
+  vec4_t<T> ao = p.ao[i];
+  const T hdt2 = mul_rn(mul_rn(T(0.5), p.dt), p.dt);
+  const T hdt  = mul_rn(T(0.5), p.dt);
+  xm.x = add_rn(xm.x, add_rn(mul_rn(v.x, p.dt), mul_rn(ao.x, hdt2)));
+  xm.y = add_rn(xm.y, add_rn(mul_rn(v.y, p.dt), mul_rn(ao.y, hdt2)));
+  if (D == 3) xm.z = add_rn(xm.z, add_rn(mul_rn(v.z, p.dt), mul_rn(ao.z, hdt2)));
+  v.x = add_rn(v.x, mul_rn(add_rn(anew.x, ao.x), hdt));
+  v.y = add_rn(v.y, mul_rn(add_rn(anew.y, ao.y), hdt));
+  if (D == 3) v.z = add_rn(v.z, mul_rn(add_rn(anew.z, ao.z), hdt));
+  p.xm_out[i] = xm;
+  p.v[i]      = v;
+  p.ao[i]     = anew;
+}
+
+template <typename T, int D>
+__global__ void accelerate_kernel(LeapArgs<T> p, uint32_t tb, uint32_t te) {
+  uint32_t i = tb + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= te) return;
+  leapfrog_body<T, D>(p, i, p.a[i]);
+}
+
+// ---- all-pairs ------------------------------------------------------------------------------------------------
+template <typename T>
+struct AllPairsArgs {
+  const vec4_t<T>* xm;   // sources (n_pad + TILE zero-mass padding records)
+  uint32_t n;            // number of sources
+  uint32_t tb, te;       // targets [tb, te)
+  uint32_t chunk;        // stride of one j-split slab in `partial`
+  uint32_t tiles_total;  // ceil(n / TILE)
+  uint32_t tiles_per_split;
+  vec4_t<T>* partial;    // [gridDim.y][chunk]
+  uint32_t* tickets;     // [gridDim.x]
+  T c;                   // System::constant
+  int fuse;              // 1: apply the leapfrog in the epilogue
+  LeapArgs<T> leap;      // leap.a is also the destination of the acceleration
+};
+
+template <typename T, int D, int TI, int BLOCK, int TILE, int STAGES, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) all_pairs_kernel(AllPairsArgs<T> p) {
+  using V4 = vec4_t<T>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  V4* tiles      = reinterpret_cast<V4*>(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + size_t(STAGES) * TILE * sizeof(V4));
+  __shared__ uint32_t s_ticket;
+
+  const int tid         = threadIdx.x;
+  const uint32_t i_base = p.tb + blockIdx.x * (BLOCK * TI) + tid;
+
+  T xi[TI], yi[TI], zi[TI], ax[TI], ay[TI], az[TI];
+#pragma unroll
+  for (int t = 0; t < TI; ++t) {
+    uint32_t i = i_base + t * BLOCK;
+    V4 b       = p.xm[i < p.te ? i : p.tb];
+    xi[t] = b.x; yi[t] = b.y; zi[t] = b.z;
+    ax[t] = ay[t] = az[t] = T(0);
+  }
+
+  const uint32_t tile_begin = blockIdx.y * p.tiles_per_split;
+  uint32_t tile_end         = tile_begin + p.tiles_per_split;
+  if (tile_end > p.tiles_total) tile_end = p.tiles_total;
+  const int ntiles = tile_end > tile_begin ? int(tile_end - tile_begin) : 0;
+
+  constexpr uint32_t TILE_BYTES = TILE * sizeof(V4);
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int s = 0; s < STAGES && s < ntiles; ++s) {
+      mbar_expect_tx(&bars[s], TILE_BYTES);
+      tma_load_1d(tiles + size_t(s) * TILE, p.xm + size_t(tile_begin + s) * TILE, TILE_BYTES, &bars[s]);
+    }
+  }
+
+  for (int k = 0; k < ntiles; ++k) {
+    const int stage = k % STAGES;
+    mbar_wait(&bars[stage], (k / STAGES) & 1);
+    const V4* tile = tiles + size_t(stage) * TILE;
+#pragma unroll 4
+    for (int j = 0; j < TILE; ++j) {
+      const V4 b = tile[j];  // broadcast LDS.128 (2x for double)
+#pragma unroll
+      for (int t = 0; t < TI; ++t) {
+        T dx = b.x - xi[t];
+        T dy = b.y - yi[t];
+        T d2 = fma(dy, dy, dx * dx);
+        T dz = T(0);
+        if (D == 3) {
+          dz = b.z - zi[t];
+          d2 = fma(dz, dz, d2);
+        }
+        T s   = b.w * inv_dist3(d2);
+        ax[t] = fma(dx, s, ax[t]);
+        ay[t] = fma(dy, s, ay[t]);
+        if (D == 3) az[t] = fma(dz, s, az[t]);
+      }
+    }
+    __syncthreads();  // every warp is done with this stage: safe to overwrite it
+    if (tid == 0 && k + STAGES < ntiles) {
+      mbar_expect_tx(&bars[stage], TILE_BYTES);
+      tma_load_1d(tiles + size_t(stage) * TILE, p.xm + size_t(tile_begin + k + STAGES) * TILE, TILE_BYTES,
+                  &bars[stage]);
+    }
+  }
+
+  // ---- epilogue: combine the j-splits in fixed order, scale by c, (optionally) leapfrog ------------------------
+  const uint32_t nsplit = gridDim.y;
+  if (nsplit > 1) {
+#pragma unroll
+    for (int t = 0; t < TI; ++t) {
+      uint32_t i = i_base + t * BLOCK;
+      if (i < p.te) stcg_v4(&p.partial[size_t(blockIdx.y) * p.chunk + (i - p.tb)], make_v4<T>(ax[t], ay[t], az[t], T(0)));
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(&p.tickets[blockIdx.x], 1u);
+    __syncthreads();
+    if (s_ticket != nsplit - 1) return;
+    __threadfence();
+    if (tid == 0) p.tickets[blockIdx.x] = 0;  // self-reset for the next launch
+#pragma unroll
+    for (int t = 0; t < TI; ++t) {
+      uint32_t i = i_base + t * BLOCK;
+      ax[t] = ay[t] = az[t] = T(0);
+      if (i < p.te) {
+        for (uint32_t s = 0; s < nsplit; ++s) {
+          V4 q = ldcg_v4(&p.partial[size_t(s) * p.chunk + (i - p.tb)]);
+          ax[t] += q.x; ay[t] += q.y; az[t] += q.z;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < TI; ++t) {
+    uint32_t i = i_base + t * BLOCK;
+    if (i >= p.te) continue;
+    V4 anew = make_v4<T>(mul_rn(ax[t], p.c), mul_rn(ay[t], p.c), D == 3 ? mul_rn(az[t], p.c) : T(0), T(0));
+    p.leap.a[i] = anew;
+    if (p.fuse) leapfrog_body<T, D>(p.leap, i, anew);
+  }
+}
+
+// ---- all-pairs-collapsed (pair-parallel) ----------------------------------------------------------------------
+// Work-item p = j*n + i of the reference becomes: lanes <-> j, 8 rows i per warp, 8 warps (64 rows) per CTA; the j
+// tile is staged in shared memory once per CTA. Each lane accumulates its partial row sums over the CTA's j range,
+// a warp-shuffle butterfly reduces them and ONE relaxed atomic per row/component/CTA lands in a[i] — the same
+// relaxed fetch_add the reference issues per pair (all_pairs.h:47-48). NC = 2 reproduces the reference's
+// two-component accumulate; NC = 3 is the opt-in fix.
+template <typename T>
+struct CollapsedArgs {
+  const vec4_t<T>* xm;
+  uint32_t n, tb, te;
+  uint32_t tiles_total, tiles_per_split;
+  vec4_t<T>* a;
+  T c;
+};
+
+template <typename T>
+__global__ void collapsed_reset_kernel(vec4_t<T>* a, const vec4_t<T>* ao, uint32_t tb, uint32_t te, int nc) {
+  uint32_t i = tb + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= te) return;
+  vec4_t<T> q = a[i], o = ao[i];
+  // all_pairs.h:35-39: "reset to zero by subtracting old acceleration"
+  q.x = add_rn(q.x, -o.x);
+  q.y = add_rn(q.y, -o.y);
+  if (nc == 3) q.z = add_rn(q.z, -o.z);
+  a[i] = q;
+}
+
+template <typename T, int D, int NC, int TILE>
+__global__ void __launch_bounds__(256) collapsed_kernel(CollapsedArgs<T> p) {
+  using V4 = vec4_t<T>;
+  constexpr int ROWS = 8;
+  __shared__ V4 tile[TILE];
+  __shared__ V4 rows[8 * ROWS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t row0 = p.tb + blockIdx.x * (8 * ROWS);
+  if (tid < 8 * ROWS) {
+    uint32_t i = row0 + tid;
+    rows[tid]  = p.xm[i < p.te ? i : p.tb];
+  }
+  T acc[ROWS][NC];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+    for (int k = 0; k < NC; ++k) acc[r][k] = T(0);
+
+  const uint32_t tile_begin = blockIdx.y * p.tiles_per_split;
+  uint32_t tile_end         = tile_begin + p.tiles_per_split;
+  if (tile_end > p.tiles_total) tile_end = p.tiles_total;
+  for (uint32_t tk = tile_begin; tk < tile_end; ++tk) {
+    __syncthreads();
+    for (int q = tid; q < TILE; q += 256) tile[q] = p.xm[size_t(tk) * TILE + q];  // zero-mass padding past n
+    __syncthreads();
+#pragma unroll 2
+    for (int jj = lane; jj < TILE; jj += 32) {
+      const V4 b = tile[jj];
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        const V4 ri = rows[warp * ROWS + r];  // broadcast
+        T dx = b.x - ri.x;
+        T dy = b.y - ri.y;
+        T d2 = fma(dy, dy, dx * dx);
+        T dz = T(0);
+        if (D == 3) {
+          dz = b.z - ri.z;
+          d2 = fma(dz, dz, d2);
+        }
+        T s       = b.w * inv_dist3(d2);
+        acc[r][0] = fma(dx, s, acc[r][0]);
+        acc[r][1] = fma(dy, s, acc[r][1]);
+        if (NC == 3) acc[r][2] = fma(dz, s, acc[r][2]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      T vsum = acc[r][k];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, off);
+      acc[r][k] = vsum;
+    }
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      uint32_t i = row0 + warp * ROWS + r;
+      if (i < p.te) {
+        T* dst = reinterpret_cast<T*>(&p.a[i]);
+#pragma unroll
+        for (int k = 0; k < NC; ++k) atomicAdd(dst + k, p.c * acc[r][k]);  // RED.ADD relaxed
+      }
+    }
+  }
+}
+
+// ---- energies (system.h:62-79) --------------------------------------------------------------------------------
+template <typename T, int D>
+__global__ void __launch_bounds__(256) energy_kernel(const vec4_t<T>* xm, const vec4_t<T>* v, uint32_t n,
+                                                      double* out /* [0]=sum m v^2, [1]=sum_i sum_j!=i mi mj / dist */) {
+  using V4 = vec4_t<T>;
+  __shared__ V4 tile[256];
+  __shared__ double red[2][8];
+  uint32_t i   = blockIdx.x * 256 + threadIdx.x;
+  V4 bi        = xm[i < n ? i : 0];
+  V4 vi        = v[i < n ? i : 0];
+  double ke    = i < n ? double(bi.w) * (double(vi.x) * vi.x + double(vi.y) * vi.y + double(vi.z) * vi.z) : 0.0;
+  double total = 0;
+  for (uint32_t j0 = 0; j0 < n; j0 += 256) {
+    __syncthreads();
+    uint32_t j        = j0 + threadIdx.x;
+    tile[threadIdx.x] = j < n ? xm[j] : make_v4<T>(0, 0, 0, 0);
+    __syncthreads();
+    uint32_t cnt = n - j0 < 256 ? n - j0 : 256;
+    for (uint32_t q = 0; q < cnt; ++q) {
+      V4 b = tile[q];
+      T dx = bi.x - b.x, dy = bi.y - b.y, dz = bi.z - b.z;
+      T d  = sqrt(dx * dx + dy * dy + dz * dz) + (sizeof(T) == 4 ? T(FLT_EPSILON) : T(DBL_EPSILON));  // vec.h:243-246
+      if (j0 + q != i) total += double(bi.w * b.w / d);
+    }
+  }
+  if (i >= n) total = 0;
+  for (int off = 16; off > 0; off >>= 1) {
+    ke += __shfl_xor_sync(0xffffffffu, ke, off);
+    total += __shfl_xor_sync(0xffffffffu, total, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = ke;
+    red[1][threadIdx.x >> 5] = total;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double k2 = 0, g2 = 0;
+    for (int w = 0; w < 8; ++w) { k2 += red[0][w]; g2 += red[1][w]; }
+    atomicAdd(&out[0], k2);
+    atomicAdd(&out[1], g2);
+  }
+}
+
+// ---- FMA-pipe peak microbenchmarks (roofline denominators; MEASURED_PEAKS.json has none for FP32/FP64) ---------
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T b) {
+  T r0 = threadIdx.x, r1 = r0 + 1, r2 = r0 + 2, r3 = r0 + 3, r4 = r0 + 4, r5 = r0 + 5, r6 = r0 + 6, r7 = r0 + 7;
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      r0 = fma(r0, a, b); r1 = fma(r1, a, b); r2 = fma(r2, a, b); r3 = fma(r3, a, b);
+      r4 = fma(r4, a, b); r5 = fma(r5, a, b); r6 = fma(r6, a, b); r7 = fma(r7, a, b);
+    }
+  }
+  T s = r0 + r1 + r2 + r3 + r4 + r5 + r6 + r7;
+  if (s == T(123456789)) out[0] = s;
+}
+
+int measure_fma_peak(int device, int precision, double* tflops) {
+  if (!tflops) return fail(NBX_ERR_INVALID, "tflops is NULL");
+  NBX_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  NBX_CUDA(cudaGetDeviceProperties(&prop, device));
+  void* out = nullptr;
+  NBX_CUDA(cudaMalloc(&out, 64));
+  cudaEvent_t e0, e1;
+  NBX_CUDA(cudaEventCreate(&e0));
+  NBX_CUDA(cudaEventCreate(&e1));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256;
+  const int iters  = precision == NBX_F32 ? 20000 : 10000;
+  double best      = 0;
+  for (int rep = 0; rep < 4; ++rep) {
+    NBX_CUDA(cudaEventRecord(e0));
+    if (precision == NBX_F32) fma_peak_kernel<float><<<blocks, threads>>>((float*)out, iters, 1.0000001f, 1e-9f);
+    else fma_peak_kernel<double><<<blocks, threads>>>((double*)out, iters, 1.0000001, 1e-9);
+    NBX_CUDA(cudaEventRecord(e1));
+    NBX_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    NBX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    double fl = 2.0 * double(blocks) * threads * double(iters) * 64.0;
+    double tf = fl / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops = best;
+  return NBX_OK;
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+template <typename T>
+static LeapArgs<T> make_leap(nbx_engine* e, bool to_next) {
+  LeapArgs<T> l;
+  l.xm_in  = static_cast<const vec4_t<T>*>(e->xm[e->cur]);
+  l.xm_out = static_cast<vec4_t<T>*>(to_next ? e->xm[e->cur ^ 1] : e->xm[e->cur]);
+  l.v      = static_cast<vec4_t<T>*>(e->v);
+  l.a      = static_cast<vec4_t<T>*>(e->a);
+  l.ao     = static_cast<vec4_t<T>*>(e->ao);
+  l.dt     = T(e->cfg.dt);
+  return l;
+}
+
+constexpr int AP_TILE   = 512;  // bodies per shared-memory tile (also the zero-mass padding appended to xm)
+constexpr int AP_STAGES = 4;
+
+template <typename T, int D, int TI, int BLOCK, int MINB>
+static int launch_all_pairs_cfg(nbx_engine* e, bool fuse, uint32_t nsplit, uint32_t tiles_per_split) {
+  auto kern = all_pairs_kernel<T, D, TI, BLOCK, AP_TILE, AP_STAGES, MINB>;
+  const size_t smem = size_t(AP_STAGES) * AP_TILE * sizeof(vec4_t<T>) + AP_STAGES * sizeof(uint64_t);
+  static bool attr_done = false;  // per template instantiation
+  if (!attr_done) {
+    NBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  const uint32_t nt      = e->te - e->tb;
+  const uint32_t iblocks = (nt + BLOCK * TI - 1) / (BLOCK * TI);
+  if (nsplit > 1) {
+    size_t need = size_t(nsplit) * e->chunk * sizeof(vec4_t<T>);
+    if (need > e->partial_bytes) {
+      if (e->partial) cudaFree(e->partial);
+      e->partial = nullptr;
+      NBX_CUDA(cudaMalloc(&e->partial, need));
+      e->partial_bytes = need;
+    }
+    if (iblocks > e->tickets_count) {
+      if (e->tickets) cudaFree(e->tickets);
+      e->tickets = nullptr;
+      NBX_CUDA(cudaMalloc(&e->tickets, sizeof(uint32_t) * iblocks));
+      NBX_CUDA(cudaMemsetAsync(e->tickets, 0, sizeof(uint32_t) * iblocks, e->stream));
+      e->tickets_count = iblocks;
+    }
+  }
+  AllPairsArgs<T> p;
+  p.xm              = static_cast<const vec4_t<T>*>(e->xm[e->cur]);
+  p.n               = e->n;
+  p.tb              = e->tb;
+  p.te              = e->te;
+  p.chunk           = e->chunk;
+  p.tiles_total     = (e->n + AP_TILE - 1) / AP_TILE;
+  p.tiles_per_split = tiles_per_split;
+  p.partial         = static_cast<vec4_t<T>*>(e->partial);
+  p.tickets         = e->tickets;
+  p.c               = T(e->cfg.G);
+  p.fuse            = fuse ? 1 : 0;
+  p.leap            = make_leap<T>(e, /*to_next=*/true);
+  dim3 grid(iblocks, nsplit);
+  kern<<<grid, BLOCK, smem, e->stream>>>(p);
+  e->launches++;
+  NBX_CUDA(cudaGetLastError());
+  return NBX_OK;
+}
+
+template <typename T, int D>
+static int launch_all_pairs(nbx_engine* e, bool fuse) {
+  const uint32_t nt = e->te - e->tb;
+  if (nt == 0) return NBX_OK;
+  const uint32_t tiles_total = (e->n + AP_TILE - 1) / AP_TILE;
+  // pick the target register blocking so that small problems still fill the chip
+  constexpr int TI_MAX = sizeof(T) == 4 ? 4 : 2;
+  int ti               = TI_MAX;
+  const uint32_t want  = uint32_t(e->sm_count) * 4;
+  while (ti > 1 && ((nt + 256 * ti - 1) / (256 * ti)) * tiles_total < want * 4) ti >>= 1;
+  const int block        = 256;
+  const uint32_t iblocks = (nt + block * ti - 1) / (block * ti);
+  // j-split: aim for >= 32 waves of CTAs (3 resident per SM) while keeping >= 4 tiles per CTA
+  uint32_t target_ctas = uint32_t(e->sm_count) * 3 * 32;
+  uint32_t nsplit      = (target_ctas + iblocks - 1) / iblocks;
+  uint32_t max_split   = tiles_total / 4 ? tiles_total / 4 : 1;
+  if (nsplit > max_split) nsplit = max_split;
+  if (nsplit < 1) nsplit = 1;
+  uint32_t tps = (tiles_total + nsplit - 1) / nsplit;
+  nsplit       = (tiles_total + tps - 1) / tps;
+  if constexpr (sizeof(T) == 4) {
+    if (ti == 4) return launch_all_pairs_cfg<T, D, 4, 256, 3>(e, fuse, nsplit, tps);
+    if (ti == 2) return launch_all_pairs_cfg<T, D, 2, 256, 3>(e, fuse, nsplit, tps);
+    return launch_all_pairs_cfg<T, D, 1, 256, 3>(e, fuse, nsplit, tps);
+  } else {
+    if (ti == 2) return launch_all_pairs_cfg<T, D, 2, 256, 2>(e, fuse, nsplit, tps);
+    return launch_all_pairs_cfg<T, D, 1, 256, 2>(e, fuse, nsplit, tps);
+  }
+}
+
+int all_pairs_force(nbx_engine* e, bool fuse_integrate) {
+  PhaseTimer pt(e, PH_FORCE);
+  int rc;
+  if (e->prec == 4) rc = e->dim == 2 ? launch_all_pairs<float, 2>(e, fuse_integrate) : launch_all_pairs<float, 3>(e, fuse_integrate);
+  else rc = e->dim == 2 ? launch_all_pairs<double, 2>(e, fuse_integrate) : launch_all_pairs<double, 3>(e, fuse_integrate);
+  if (rc == NBX_OK && fuse_integrate) e->cur ^= 1;
+  return rc;
+}
+
+template <typename T, int D>
+static int launch_collapsed(nbx_engine* e) {
+  const uint32_t nt = e->te - e->tb;
+  if (nt == 0) return NBX_OK;
+  constexpr int TILE = 512;
+  const int nc       = (e->cfg.flags & NBX_FLAG_COLLAPSED_FIX_Z) && D == 3 ? 3 : 2;
+  collapsed_reset_kernel<T><<<(nt + 255) / 256, 256, 0, e->stream>>>(static_cast<vec4_t<T>*>(e->a),
+                                                                     static_cast<const vec4_t<T>*>(e->ao), e->tb, e->te, nc);
+  e->launches++;
+  CollapsedArgs<T> p;
+  p.xm          = static_cast<const vec4_t<T>*>(e->xm[e->cur]);
+  p.n           = e->n;
+  p.tb          = e->tb;
+  p.te          = e->te;
+  p.tiles_total = (e->n + TILE - 1) / TILE;
+  p.a           = static_cast<vec4_t<T>*>(e->a);
+  p.c           = T(e->cfg.G);
+  const uint32_t rblocks = (nt + 63) / 64;
+  uint32_t target_ctas   = uint32_t(e->sm_count) * 4 * 16;
+  uint32_t nsplit        = (target_ctas + rblocks - 1) / rblocks;
+  uint32_t max_split     = p.tiles_total / 2 ? p.tiles_total / 2 : 1;
+  if (nsplit > max_split) nsplit = max_split;
+  if (nsplit < 1) nsplit = 1;
+  p.tiles_per_split = (p.tiles_total + nsplit - 1) / nsplit;
+  nsplit            = (p.tiles_total + p.tiles_per_split - 1) / p.tiles_per_split;
+  dim3 grid(rblocks, nsplit);
+  if (nc == 3) collapsed_kernel<T, D, 3, TILE><<<grid, 256, 0, e->stream>>>(p);
+  else collapsed_kernel<T, D, 2, TILE><<<grid, 256, 0, e->stream>>>(p);
+  e->launches++;
+  NBX_CUDA(cudaGetLastError());
+  return NBX_OK;
+}
+
+int all_pairs_collapsed_force(nbx_engine* e) {
+  PhaseTimer pt(e, PH_FORCE);
+  if (e->prec == 4) return e->dim == 2 ? launch_collapsed<float, 2>(e) : launch_collapsed<float, 3>(e);
+  return e->dim == 2 ? launch_collapsed<double, 2>(e) : launch_collapsed<double, 3>(e);
+}
+
+template <typename T, int D>
+static int launch_accelerate(nbx_engine* e) {
+  const uint32_t nt = e->te - e->tb;
+  if (nt == 0) return NBX_OK;
+  accelerate_kernel<T, D><<<(nt + 255) / 256, 256, 0, e->stream>>>(make_leap<T>(e, /*to_next=*/false), e->tb, e->te);
+  e->launches++;
+  NBX_CUDA(cudaGetLastError());
+  return NBX_OK;
+}
+
+int accelerate_step(nbx_engine* e) {
+  PhaseTimer pt(e, PH_ACCEL);
+  if (e->prec == 4) return e->dim == 2 ? launch_accelerate<float, 2>(e) : launch_accelerate<float, 3>(e);
+  return e->dim == 2 ? launch_accelerate<double, 2>(e) : launch_accelerate<double, 3>(e);
+}
+
+template <typename T, int D>
+static int launch_energies(nbx_engine* e, double* out_dev) {
+  energy_kernel<T, D><<<(e->n + 255) / 256, 256, 0, e->stream>>>(static_cast<const vec4_t<T>*>(e->xm[e->cur]),
+                                                                 static_cast<const vec4_t<T>*>(e->v), e->n, out_dev);
+  e->launches++;
+  NBX_CUDA(cudaGetLastError());
+  return NBX_OK;
+}
+
+int calc_energies(nbx_engine* e, double* kinetic, double* grav) {
+  double* out = nullptr;
+  NBX_CUDA(cudaMalloc(&out, 2 * sizeof(double)));
+  NBX_CUDA(cudaMemsetAsync(out, 0, 2 * sizeof(double), e->stream));
+  int rc;
+  if (e->prec == 4) rc = e->dim == 2 ? launch_energies<float, 2>(e, out) : launch_energies<float, 3>(e, out);
+  else rc = e->dim == 2 ? launch_energies<double, 2>(e, out) : launch_energies<double, 3>(e, out);
+  double h[2] = {0, 0};
+  if (rc == NBX_OK) {
+    cudaError_t err = cudaMemcpyAsync(h, out, sizeof(h), cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    if (err != cudaSuccess) rc = fail(NBX_ERR_CUDA, cudaGetErrorString(err));
+    e->d2h += sizeof(h);
+  }
+  cudaFree(out);
+  if (rc != NBX_OK) return rc;
+  if (kinetic) *kinetic = 0.5 * h[0];               // system.h:64-66
+  if (grav) *grav = -0.5 * e->cfg.G * h[1];         // system.h:67-77
+  return NBX_OK;
+}
+
+}  // namespace nbx

@@ -1,0 +1,94 @@
+// nbx_comm.cu — multi-GPU exchange of positions (one process per GPU, NCCL over NVLink 5 / NVSwitch).
+//
+// The reference has no distributed code; this is new work: targets are sharded by rank
+// (rank r owns [r*chunk, (r+1)*chunk)), every rank keeps all sources, and after each step the new positions of
+// the local shard are all-gathered IN PLACE into the (x,y,z,m) buffer. NCCL is loaded with dlopen so that the
+// single-GPU library has no link-time dependency (inside a torch process this resolves to torch's bundled
+// libnccl.so.2, in the C++ driver to the system one).
+#include <dlfcn.h>
+
+#include "nbx_internal.cuh"
+
+namespace nbx {
+
+namespace {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+constexpr int ncclChar = 0;
+
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*)                                                           = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int)                                     = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t)                                                               = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t)                  = nullptr;
+  const char* (*GetErrorString)(ncclResult_t)                                                           = nullptr;
+  bool ok = false;
+};
+
+NcclApi& api() {
+  static NcclApi a;
+  static bool tried = false;
+  if (tried) return a;
+  tried = true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    a.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (a.lib) break;
+  }
+  if (!a.lib) return a;
+  a.GetUniqueId    = (decltype(a.GetUniqueId))dlsym(a.lib, "ncclGetUniqueId");
+  a.CommInitRank   = (decltype(a.CommInitRank))dlsym(a.lib, "ncclCommInitRank");
+  a.CommDestroy    = (decltype(a.CommDestroy))dlsym(a.lib, "ncclCommDestroy");
+  a.AllGather      = (decltype(a.AllGather))dlsym(a.lib, "ncclAllGather");
+  a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.lib, "ncclGetErrorString");
+  a.ok             = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.GetErrorString;
+  return a;
+}
+
+int nccl_fail(const char* what, ncclResult_t r) {
+  return fail(NBX_ERR_COMM, std::string(what) + ": " + (api().GetErrorString ? api().GetErrorString(r) : "nccl error"));
+}
+}  // namespace
+
+int comm_unique_id(void* id128) {
+  if (!id128) return fail(NBX_ERR_INVALID, "id128 is NULL");
+  if (!api().ok) return fail(NBX_ERR_COMM, "libnccl.so.2 could not be loaded");
+  ncclUniqueId id;
+  ncclResult_t r = api().GetUniqueId(&id);
+  if (r != 0) return nccl_fail("ncclGetUniqueId", r);
+  memcpy(id128, &id, sizeof(id));
+  return NBX_OK;
+}
+
+int comm_init_rank(nbx_engine* e, const void* id128) {
+  if (!id128) return fail(NBX_ERR_INVALID, "id128 is NULL");
+  if (e->cfg.world_size <= 1) return NBX_OK;
+  if (!api().ok) return fail(NBX_ERR_COMM, "libnccl.so.2 could not be loaded");
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  ncclComm_t c   = nullptr;
+  ncclResult_t r = api().CommInitRank(&c, e->cfg.world_size, id, e->cfg.rank);
+  if (r != 0) return nccl_fail("ncclCommInitRank", r);
+  e->comm = c;
+  return NBX_OK;
+}
+
+int comm_allgather_positions(nbx_engine* e) {
+  if (e->cfg.world_size <= 1) return NBX_OK;
+  if (!e->comm) return fail(NBX_ERR_COMM, "multi-GPU engine used before nbx_comm_init_rank");
+  PhaseTimer pt(e, PH_COMM);
+  char* base         = static_cast<char*>(e->xm[e->cur]);
+  const size_t bytes = rec_bytes(e) * e->chunk;
+  ncclResult_t r = api().AllGather(base + bytes * e->cfg.rank, base, bytes, ncclChar, (ncclComm_t)e->comm, e->stream);
+  if (r != 0) return nccl_fail("ncclAllGather", r);
+  return NBX_OK;
+}
+
+void comm_destroy(nbx_engine* e) {
+  if (e->comm && api().ok) api().CommDestroy((ncclComm_t)e->comm);
+  e->comm = nullptr;
+}
+
+}  // namespace nbx

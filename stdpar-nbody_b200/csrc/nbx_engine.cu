@@ -1,0 +1,427 @@
+// nbx_engine.cu — engine lifetime, host<->device state transfer, step drivers and the extern "C" surface of nbx.h.
+#include <cstring>
+#include <mutex>
+
+#include "nbx_internal.cuh"
+
+namespace nbx {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+// ---- AoS (state_t, src/system.h:41-50) <-> vec4 records -------------------------------------------------------
+// pack: stage holds T m[n] | T q[n*D]  ->  xm[i] = (x, y, z|0, m)   or   vec[i] = (q0, q1, q2|0, 0)
+template <typename T, int D>
+__global__ void pack_pos_kernel(const T* __restrict__ x, vec4_t<T>* xm, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  vec4_t<T> r = xm[i];
+  r.x = x[size_t(i) * D];
+  r.y = x[size_t(i) * D + 1];
+  r.z = D == 3 ? x[size_t(i) * D + 2] : T(0);
+  xm[i] = r;
+}
+template <typename T>
+__global__ void pack_mass_kernel(const T* __restrict__ m, vec4_t<T>* xm, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  vec4_t<T> r = xm[i];
+  r.w = m[i];
+  xm[i] = r;
+}
+template <typename T, int D>
+__global__ void pack_vec_kernel(const T* __restrict__ q, vec4_t<T>* out, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = make_v4<T>(q[size_t(i) * D], q[size_t(i) * D + 1], D == 3 ? q[size_t(i) * D + 2] : T(0), T(0));
+}
+template <typename T, int D>
+__global__ void unpack_vec_kernel(const vec4_t<T>* __restrict__ in, T* q, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  vec4_t<T> r = in[i];
+  q[size_t(i) * D]     = r.x;
+  q[size_t(i) * D + 1] = r.y;
+  if (D == 3) q[size_t(i) * D + 2] = r.z;
+}
+template <typename T>
+__global__ void unpack_mass_kernel(const vec4_t<T>* __restrict__ in, T* m, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  m[i] = in[i].w;
+}
+
+static int ensure_stage(nbx_engine* e, size_t bytes) {
+  if (bytes <= e->stage_bytes) return NBX_OK;
+  if (e->stage) cudaFree(e->stage);
+  e->stage = nullptr;
+  NBX_CUDA(cudaMalloc(&e->stage, bytes));
+  e->stage_bytes = bytes;
+  return NBX_OK;
+}
+
+template <typename T, int D>
+static int upload_impl(nbx_engine* e, const void* m, const void* x, const void* v, const void* a, const void* ao) {
+  const uint32_t n = e->n;
+  const dim3 grid((n + 255) / 256), block(256);
+  NBX_TRY(ensure_stage(e, sizeof(T) * size_t(n) * D));
+  auto put = [&](const void* host, size_t bytes) -> int {
+    NBX_CUDA(cudaMemcpyAsync(e->stage, host, bytes, cudaMemcpyHostToDevice, e->stream));
+    e->h2d += bytes;
+    return NBX_OK;
+  };
+  if (x) {
+    NBX_TRY(put(x, sizeof(T) * size_t(n) * D));
+    pack_pos_kernel<T, D><<<grid, block, 0, e->stream>>>((const T*)e->stage, (vec4_t<T>*)e->xm[e->cur], n);
+    e->launches++;
+  }
+  if (m) {
+    NBX_TRY(put(m, sizeof(T) * size_t(n)));
+    pack_mass_kernel<T><<<grid, block, 0, e->stream>>>((const T*)e->stage, (vec4_t<T>*)e->xm[e->cur], n);
+    e->launches++;
+  }
+  if (x || m) {
+    // both position buffers carry the masses (the fused leapfrog writes x,m into the other one)
+    NBX_CUDA(cudaMemcpyAsync(e->xm[e->cur ^ 1], e->xm[e->cur], rec_bytes(e) * n, cudaMemcpyDeviceToDevice, e->stream));
+  }
+  const void* src[3] = {v, a, ao};
+  void* dst[3]       = {e->v, e->a, e->ao};
+  for (int q = 0; q < 3; ++q) {
+    if (!src[q]) continue;
+    NBX_TRY(put(src[q], sizeof(T) * size_t(n) * D));
+    pack_vec_kernel<T, D><<<grid, block, 0, e->stream>>>((const T*)e->stage, (vec4_t<T>*)dst[q], n);
+    e->launches++;
+  }
+  NBX_CUDA(cudaGetLastError());
+  NBX_CUDA(cudaStreamSynchronize(e->stream));  // host arrays may be reused by the caller
+  return NBX_OK;
+}
+
+template <typename T, int D>
+static int download_impl(nbx_engine* e, void* m, void* x, void* v, void* a, void* ao) {
+  const uint32_t n = e->n;
+  const dim3 grid((n + 255) / 256), block(256);
+  NBX_TRY(ensure_stage(e, sizeof(T) * size_t(n) * D));
+  auto get = [&](void* host, size_t bytes) -> int {
+    NBX_CUDA(cudaMemcpyAsync(host, e->stage, bytes, cudaMemcpyDeviceToHost, e->stream));
+    NBX_CUDA(cudaStreamSynchronize(e->stream));
+    e->d2h += bytes;
+    return NBX_OK;
+  };
+  if (m) {
+    unpack_mass_kernel<T><<<grid, block, 0, e->stream>>>((const vec4_t<T>*)e->xm[e->cur], (T*)e->stage, n);
+    e->launches++;
+    NBX_TRY(get(m, sizeof(T) * size_t(n)));
+  }
+  void* dsth[4]      = {x, v, a, ao};
+  const void* src[4] = {e->xm[e->cur], e->v, e->a, e->ao};
+  for (int q = 0; q < 4; ++q) {
+    if (!dsth[q]) continue;
+    unpack_vec_kernel<T, D><<<grid, block, 0, e->stream>>>((const vec4_t<T>*)src[q], (T*)e->stage, n);
+    e->launches++;
+    NBX_TRY(get(dsth[q], sizeof(T) * size_t(n) * D));
+  }
+  NBX_CUDA(cudaGetLastError());
+  return NBX_OK;
+}
+
+#define NBX_DISPATCH(e, fn, ...)                                                          \
+  ((e)->prec == 4 ? ((e)->dim == 2 ? fn<float, 2>(__VA_ARGS__) : fn<float, 3>(__VA_ARGS__)) \
+                  : ((e)->dim == 2 ? fn<double, 2>(__VA_ARGS__) : fn<double, 3>(__VA_ARGS__)))
+
+// ---- one time step (the `kernels()` lambda of the reference drivers) -------------------------------------------
+static int one_step(nbx_engine* e) {
+  const bool multi = e->cfg.world_size > 1;
+  switch (e->algo) {
+    case NBX_ALL_PAIRS: {
+      const bool fuse = !(e->cfg.flags & NBX_FLAG_NO_FUSED_INTEGRATE);
+      NBX_TRY(all_pairs_force(e, fuse));
+      if (!fuse) NBX_TRY(accelerate_step(e));
+      break;
+    }
+    case NBX_ALL_PAIRS_COLLAPSED:
+      NBX_TRY(all_pairs_collapsed_force(e));
+      NBX_TRY(accelerate_step(e));
+      break;
+    case NBX_BVH:
+      NBX_TRY(bvh_bounding_box(e));
+      NBX_TRY(bvh_hilbert_sort(e));
+      NBX_TRY(bvh_build_tree(e));
+      NBX_TRY(bvh_compute_force(e));
+      NBX_TRY(accelerate_step(e));
+      break;
+    case NBX_OCTREE:
+      NBX_TRY(octree_build(e));
+      NBX_TRY(octree_compute_force(e));
+      NBX_TRY(accelerate_step(e));
+      break;
+    default: return fail(NBX_ERR_INVALID, "unknown algorithm");
+  }
+  if (multi) NBX_TRY(comm_allgather_positions(e));
+  return NBX_OK;
+}
+
+static void collect_phase_times(nbx_engine* e) {
+  if (!e->phase_timing) return;
+  for (int s = 0; s < PH_COUNT; ++s) {
+    e->ph_ms[s] = 0;
+    if (e->ph_used[s]) cudaEventElapsedTime(&e->ph_ms[s], e->ph_ev[s][0], e->ph_ev[s][1]);
+  }
+}
+
+}  // namespace nbx
+
+using namespace nbx;
+
+// =================================================================================================================
+extern "C" {
+
+const char* nbx_last_error(void) { return g_last_error.c_str(); }
+int nbx_version(void) { return NBX_VERSION; }
+
+int nbx_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int nbx_create(const nbx_config* cfg, nbx_engine** out) {
+  if (!cfg || !out) return fail(NBX_ERR_INVALID, "nbx_create: NULL argument");
+  *out = nullptr;
+  if (cfg->struct_size != sizeof(nbx_config)) return fail(NBX_ERR_INVALID, "nbx_create: struct_size mismatch");
+  if (cfg->dim != 2 && cfg->dim != 3)
+    return fail(NBX_ERR_INVALID, "nbx_create: dim must be 2 or 3 (reference: -DDIM_SIZE, src/main.cpp:5-7)");
+  if (cfg->precision != NBX_F32 && cfg->precision != NBX_F64)
+    return fail(NBX_ERR_INVALID, "nbx_create: precision must be NBX_F32 or NBX_F64");
+  if (cfg->algorithm < NBX_ALL_PAIRS || cfg->algorithm > NBX_BVH) return fail(NBX_ERR_INVALID, "nbx_create: unknown algorithm");
+  if (cfg->n == 0) return fail(NBX_ERR_INVALID, "nbx_create: n must be > 0");
+  if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size)
+    return fail(NBX_ERR_INVALID, "nbx_create: bad rank/world_size");
+  if (cfg->algorithm == NBX_BVH && cfg->n < 2) return fail(NBX_ERR_INVALID, "nbx_create: bvh needs n >= 2");
+  int ndev = nbx_device_count();
+  if (ndev <= 0) return fail(NBX_ERR_NO_DEVICE, "nbx_create: no CUDA device (libnbx has no CPU path)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(NBX_ERR_INVALID, "nbx_create: device ordinal out of range");
+
+  nbx_engine* e = new nbx_engine();
+  e->cfg  = *cfg;
+  e->dim  = cfg->dim;
+  e->prec = cfg->precision;
+  e->algo = cfg->algorithm;
+  e->n    = cfg->n;
+  e->device = cfg->device;
+  e->chunk  = (cfg->n + cfg->world_size - 1) / cfg->world_size;
+  e->n_pad  = e->chunk * cfg->world_size;
+  e->tb     = std::min<uint64_t>(uint64_t(e->chunk) * cfg->rank, cfg->n);
+  e->te     = std::min<uint64_t>(uint64_t(e->chunk) * (cfg->rank + 1), cfg->n);
+  auto bail = [&](int rc) { nbx_destroy(e); return rc; };
+#define NBX_CUDA_B(call)                                                                          \
+  do {                                                                                            \
+    cudaError_t err__ = (call);                                                                   \
+    if (err__ != cudaSuccess) return bail(fail(NBX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__))); \
+  } while (0)
+  NBX_CUDA_B(cudaSetDevice(e->device));
+  cudaDeviceProp prop;
+  NBX_CUDA_B(cudaGetDeviceProperties(&prop, e->device));
+  e->sm_count = prop.multiProcessorCount;
+  NBX_CUDA_B(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  NBX_CUDA_B(cudaEventCreate(&e->ev0));
+  NBX_CUDA_B(cudaEventCreate(&e->ev1));
+  for (int s = 0; s < PH_COUNT; ++s)
+    for (int k = 0; k < 2; ++k) NBX_CUDA_B(cudaEventCreate(&e->ph_ev[s][k]));
+  const size_t rb = rec_bytes(e);
+  // position buffers carry a zero-mass tail (n_pad - n records of padding + one all-pairs tile) so that tile
+  // loads never need a bounds check: a zero-mass source contributes exactly 0.
+  const size_t pos_records = size_t(e->n_pad) + 1024;
+  for (int k = 0; k < 2; ++k) {
+    NBX_CUDA_B(cudaMalloc(&e->xm[k], rb * pos_records));
+    NBX_CUDA_B(cudaMemsetAsync(e->xm[k], 0, rb * pos_records, e->stream));
+  }
+  void** vecs[3] = {&e->v, &e->a, &e->ao};
+  for (auto pp : vecs) {
+    NBX_CUDA_B(cudaMalloc(pp, rb * e->n));
+    NBX_CUDA_B(cudaMemsetAsync(*pp, 0, rb * e->n, e->stream));
+  }
+  int rc = NBX_OK;
+  if (e->algo == NBX_BVH) rc = bvh_create(e);
+  if (e->algo == NBX_OCTREE) rc = octree_create(e);
+  if (rc != NBX_OK) return bail(rc);
+  NBX_CUDA_B(cudaStreamSynchronize(e->stream));
+#undef NBX_CUDA_B
+  *out = e;
+  return NBX_OK;
+}
+
+int nbx_destroy(nbx_engine* e) {
+  if (!e) return NBX_OK;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  comm_destroy(e);
+  bvh_destroy(e);
+  octree_destroy(e);
+  sorter_destroy(e);
+  void* bufs[] = {e->xm[0], e->xm[1], e->v, e->a, e->ao, e->v_alt, e->a_alt, e->ao_alt, e->partial, e->tickets, e->stage};
+  for (void* b : bufs)
+    if (b) cudaFree(b);
+  if (e->pinned) cudaFreeHost(e->pinned);
+  for (int s = 0; s < PH_COUNT; ++s)
+    for (int k = 0; k < 2; ++k)
+      if (e->ph_ev[s][k]) cudaEventDestroy(e->ph_ev[s][k]);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+  return NBX_OK;
+}
+
+#define NBX_ENTER(e)                                                   \
+  if (!(e)) return fail(NBX_ERR_INVALID, std::string(__func__) + ": NULL engine"); \
+  NBX_CUDA(cudaSetDevice((e)->device))
+
+int nbx_upload(nbx_engine* e, const void* m, const void* x, const void* v, const void* a, const void* ao) {
+  NBX_ENTER(e);
+  return NBX_DISPATCH(e, upload_impl, e, m, x, v, a, ao);
+}
+
+int nbx_download(nbx_engine* e, void* m, void* x, void* v, void* a, void* ao) {
+  NBX_ENTER(e);
+  return NBX_DISPATCH(e, download_impl, e, m, x, v, a, ao);
+}
+
+int nbx_step(nbx_engine* e, uint32_t steps) {
+  NBX_ENTER(e);
+  for (uint32_t s = 0; s < steps; ++s) NBX_TRY(one_step(e));
+  return NBX_OK;
+}
+
+int nbx_step_timed(nbx_engine* e, uint32_t steps, float* ms) {
+  NBX_ENTER(e);
+  NBX_CUDA(cudaEventRecord(e->ev0, e->stream));
+  for (uint32_t s = 0; s < steps; ++s) NBX_TRY(one_step(e));
+  NBX_CUDA(cudaEventRecord(e->ev1, e->stream));
+  NBX_CUDA(cudaEventSynchronize(e->ev1));
+  if (ms) NBX_CUDA(cudaEventElapsedTime(ms, e->ev0, e->ev1));
+  collect_phase_times(e);
+  return NBX_OK;
+}
+
+int nbx_sync(nbx_engine* e) {
+  NBX_ENTER(e);
+  NBX_CUDA(cudaStreamSynchronize(e->stream));
+  collect_phase_times(e);
+  return NBX_OK;
+}
+
+int nbx_all_pairs_force(nbx_engine* e) {
+  NBX_ENTER(e);
+  return all_pairs_force(e, false);
+}
+int nbx_all_pairs_collapsed_force(nbx_engine* e) {
+  NBX_ENTER(e);
+  return all_pairs_collapsed_force(e);
+}
+int nbx_accelerate_step(nbx_engine* e) {
+  NBX_ENTER(e);
+  return accelerate_step(e);
+}
+int nbx_calc_energies(nbx_engine* e, double* kinetic, double* gravitational) {
+  NBX_ENTER(e);
+  return calc_energies(e, kinetic, gravitational);
+}
+
+int nbx_bvh_bounding_box(nbx_engine* e, void* xmin, void* xmax) {
+  NBX_ENTER(e);
+  if (e->algo != NBX_BVH) return fail(NBX_ERR_STATE, "engine was not created with NBX_BVH");
+  NBX_TRY(bvh_bounding_box(e));
+  if (xmin || xmax) return bvh_get_bbox(e, xmin, xmax);
+  return NBX_OK;
+}
+int nbx_bvh_hilbert_sort(nbx_engine* e) {
+  NBX_ENTER(e);
+  if (e->algo != NBX_BVH) return fail(NBX_ERR_STATE, "engine was not created with NBX_BVH");
+  return bvh_hilbert_sort(e);
+}
+int nbx_bvh_build_tree(nbx_engine* e) {
+  NBX_ENTER(e);
+  if (e->algo != NBX_BVH) return fail(NBX_ERR_STATE, "engine was not created with NBX_BVH");
+  return bvh_build_tree(e);
+}
+int nbx_bvh_compute_force(nbx_engine* e) {
+  NBX_ENTER(e);
+  if (e->algo != NBX_BVH) return fail(NBX_ERR_STATE, "engine was not created with NBX_BVH");
+  return bvh_compute_force(e);
+}
+int nbx_bvh_get_keys(nbx_engine* e, uint64_t* keys, uint32_t* perm) {
+  NBX_ENTER(e);
+  if (e->algo != NBX_BVH) return fail(NBX_ERR_STATE, "engine was not created with NBX_BVH");
+  return bvh_get_keys(e, keys, perm);
+}
+int nbx_bvh_get_nodes(nbx_engine* e, uint64_t* nnodes, void* node_m, void* bw, void* b) {
+  NBX_ENTER(e);
+  if (e->algo != NBX_BVH) return fail(NBX_ERR_STATE, "engine was not created with NBX_BVH");
+  return bvh_get_nodes(e, nnodes, node_m, bw, b);
+}
+
+int nbx_octree_build(nbx_engine* e) {
+  NBX_ENTER(e);
+  if (e->algo != NBX_OCTREE) return fail(NBX_ERR_STATE, "engine was not created with NBX_OCTREE");
+  return octree_build(e);
+}
+int nbx_octree_compute_force(nbx_engine* e) {
+  NBX_ENTER(e);
+  if (e->algo != NBX_OCTREE) return fail(NBX_ERR_STATE, "engine was not created with NBX_OCTREE");
+  return octree_compute_force(e);
+}
+int nbx_octree_get_root(nbx_engine* e, void* side, void* root_x, uint64_t* nodes_used) {
+  NBX_ENTER(e);
+  if (e->algo != NBX_OCTREE) return fail(NBX_ERR_STATE, "engine was not created with NBX_OCTREE");
+  return octree_get_root(e, side, root_x, nodes_used);
+}
+int nbx_octree_get_canonical(nbx_engine* e, uint64_t* count, uint32_t* depth, uint64_t* path, uint32_t* kind,
+                             void* monopole) {
+  NBX_ENTER(e);
+  if (e->algo != NBX_OCTREE) return fail(NBX_ERR_STATE, "engine was not created with NBX_OCTREE");
+  return octree_get_canonical(e, count, depth, path, kind, monopole);
+}
+
+int nbx_comm_unique_id(void* id128) { return comm_unique_id(id128); }
+int nbx_comm_init_rank(nbx_engine* e, const void* id128) {
+  NBX_ENTER(e);
+  return comm_init_rank(e, id128);
+}
+
+int nbx_measure_fma_peak(int device, int precision, double* tflops) {
+  if (nbx_device_count() <= 0) return fail(NBX_ERR_NO_DEVICE, "no CUDA device");
+  return measure_fma_peak(device, precision, tflops);
+}
+
+int nbx_get_counters(nbx_engine* e, uint64_t* kernel_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
+  if (!e) return fail(NBX_ERR_INVALID, "NULL engine");
+  if (kernel_launches) *kernel_launches = e->launches;
+  if (h2d_bytes) *h2d_bytes = e->h2d;
+  if (d2h_bytes) *d2h_bytes = e->d2h;
+  return NBX_OK;
+}
+
+int nbx_set_phase_timing(nbx_engine* e, int enable) {
+  if (!e) return fail(NBX_ERR_INVALID, "NULL engine");
+  e->phase_timing = enable != 0;
+  for (int s = 0; s < PH_COUNT; ++s) e->ph_used[s] = false;
+  return NBX_OK;
+}
+
+int nbx_get_phase_ms(nbx_engine* e, float* ms, int capacity, int* count) {
+  if (!e || !ms) return fail(NBX_ERR_INVALID, "NULL argument");
+  int k = 0;
+  for (int s = 0; s < PH_COUNT && k < capacity; ++s) ms[k++] = e->ph_used[s] ? e->ph_ms[s] : 0.f;
+  if (count) *count = k;
+  return NBX_OK;
+}
+
+}  // extern "C"
