@@ -80,6 +80,22 @@ class Oracle:
             C.c_uint32(n), ct(G), _p(m), _p(x), C.c_uint32(len(targets)), _p(targets), _p(a))
         return a
 
+    def all_pairs_force_truth(self, m, x, G, targets=None):
+        """The formula of all_pairs.h:14-27 in DOUBLE arithmetic with eps of x's own precision (see the C file)."""
+        n, dim = x.shape
+        eps = float(np.finfo(x.dtype).eps)
+        m64, x64 = np.ascontiguousarray(m, np.float64), np.ascontiguousarray(x, np.float64)
+        f = getattr(self.lib, f"nbo_all_pairs_force_eps_d{dim}")
+        f.restype = None
+        if targets is None:
+            a = np.empty_like(x64)
+            f(C.c_uint32(n), C.c_double(G), C.c_double(eps), _p(m64), _p(x64), C.c_uint32(0), None, _p(a))
+            return a
+        targets = np.ascontiguousarray(targets, np.uint32)
+        a = np.empty((len(targets), dim), np.float64)
+        f(C.c_uint32(n), C.c_double(G), C.c_double(eps), _p(m64), _p(x64), C.c_uint32(len(targets)), _p(targets), _p(a))
+        return a
+
     # all_pairs.h:29-50 (updates a in place, returns it)
     def collapsed_force(self, m, x, a, ao, G):
         n, dim = x.shape

@@ -1,0 +1,576 @@
+// nbx_bvh.cu — Hilbert-sorted implicit-BVH Barnes-Hut for sm_100a.
+//
+//   bbox kernels        : reference bounding_box            (src/bvh.h:17-22, src/vec.h:381-405)   [K10]
+//   hilbert_keys_kernel : reference hilbert_sort, key part  (src/bvh.h:33-45, src/vec.h:266-356)   [K11]
+//   sort_pairs          : reference std::sort               (src/bvh.h:62-69)  -> nbx_sort.cu     [K12]
+//   gather_kernel       : reference permutation copy        (src/bvh.h:71-91)                      [K13]
+//   build kernels       : reference bvh::build_tree         (src/bvh.h:175-244)                    [K14/K15]
+//   force_kernel        : reference bvh::compute_force      (src/bvh.h:246-324)                    [K16]
+//
+// Everything that feeds an integer artefact or a tree node (bbox, cell index, key, centre of mass, AABB, width) is
+// computed with explicit round-to-nearest intrinsics in the reference's association order (no FMA contraction), so
+// keys, permutation and node arrays are BIT-EXACT against the pinned oracle. The traversal evaluates the acceptance
+// test `bw^2 < theta^2 * dist2` with the same exact arithmetic (identical interaction sets) and only the accumulated
+// force uses the fast MUFU path (tolerance-level difference).
+#include <cfloat>
+
+#include "nbx_internal.cuh"
+
+namespace nbx {
+
+namespace {
+
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ uint32_t to_u32_sat(float q) { return __float2uint_rz(q); }    // cvt.rzi.u32.f32 saturates
+__device__ __forceinline__ uint32_t to_u32_sat(double q) { return __double2uint_rz(q); }  // 
+
+template <typename T>
+__host__ __device__ constexpr T eps_of() {
+  return sizeof(T) == 4 ? T(FLT_EPSILON) : T(DBL_EPSILON);
+}
+// vec.h:388: tol = (T)(epsilon * 10.)  (double product, then converted)
+template <typename T>
+__host__ __device__ inline T aabb_tol() {
+  return sizeof(T) == 4 ? T(double(FLT_EPSILON) * 10.) : T(DBL_EPSILON * 10.);
+}
+
+template <typename T>
+struct Box {  // device-resident result of the bbox reduction
+  T lo[4], hi[4], cell[4];
+};
+
+template <typename T>
+struct BvhState {
+  uint32_t levels = 0;      // log2(bit_ceil(n)); tree levels 0..levels-1, bodies are level `levels`
+  uint64_t nnodes = 0;      // 2^levels - 1
+  Box<T>* box     = nullptr;
+  T* partial      = nullptr;  // [blocks][8] partial min/max
+  uint32_t nblocks = 0;
+  uint64_t* keys   = nullptr;  // keys in entry order
+  uint32_t* perm   = nullptr;
+  vec4_t<T>* node_m = nullptr;  // (com.x, com.y, com.z, mass)
+  T* bw             = nullptr;
+  vec4_t<T>* lo     = nullptr;
+  vec4_t<T>* hi     = nullptr;
+  bool have_box = false, sorted = false, built = false;
+};
+
+// ---- K10 bounding box ------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T tmin(T a, T b) { return fmin(a, b); }
+template <typename T>
+__device__ __forceinline__ T tmax(T a, T b) { return fmax(a, b); }
+
+template <typename T, int D>
+__global__ void __launch_bounds__(256) bbox_partial_kernel(const vec4_t<T>* __restrict__ xm, uint32_t n, T* partial) {
+  T lo[3] = {T(0), T(0), T(0)}, hi[3] = {T(0), T(0), T(0)};  // identity: the origin (bvh.h:20)
+  for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    vec4_t<T> b = xm[i];
+    lo[0] = tmin(lo[0], b.x); hi[0] = tmax(hi[0], b.x);
+    lo[1] = tmin(lo[1], b.y); hi[1] = tmax(hi[1], b.y);
+    if (D == 3) { lo[2] = tmin(lo[2], b.z); hi[2] = tmax(hi[2], b.z); }
+  }
+  __shared__ T red[8][6];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      lo[k] = tmin(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], off));
+      hi[k] = tmax(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], off));
+    }
+  if ((threadIdx.x & 31) == 0)
+    for (int k = 0; k < 3; ++k) { red[threadIdx.x >> 5][k] = lo[k]; red[threadIdx.x >> 5][3 + k] = hi[k]; }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    T v = red[0][threadIdx.x];
+    for (int w = 1; w < 8; ++w) v = threadIdx.x < 3 ? tmin(v, red[w][threadIdx.x]) : tmax(v, red[w][threadIdx.x]);
+    partial[blockIdx.x * 8 + threadIdx.x] = v;
+  }
+}
+
+// final reduce + inflate + grid cell size (bvh.h:33-34). min_i(x_i - tol) == (min_i x_i) - tol because x - tol is
+// monotone under round-to-nearest, so reducing first and inflating once is exact.
+template <typename T, int D>
+__global__ void bbox_final_kernel(const T* partial, uint32_t nblocks, Box<T>* box) {
+  int k = threadIdx.x;  // one thread per axis
+  if (k >= 3) return;
+  T lo = partial[k], hi = partial[3 + k];
+  for (uint32_t b = 1; b < nblocks; ++b) {
+    lo = tmin(lo, partial[b * 8 + k]);
+    hi = tmax(hi, partial[b * 8 + 3 + k]);
+  }
+  const T tol = aabb_tol<T>();
+  lo = tmin(sub_rn(T(0), tol), sub_rn(lo, tol));
+  hi = tmax(add_rn(T(0), tol), add_rn(hi, tol));
+  const T cells = D == 2 ? T(0xffffffffu) : T(0x1fffffu);
+  box->lo[k]   = lo;
+  box->hi[k]   = hi;
+  box->cell[k] = div_rn(sub_rn(hi, lo), cells);
+}
+
+// ---- K11 Hilbert keys ------------------------------------------------------------------------------------------
+// Skilling, "Programming the Hilbert curve" (AIP Conf. Proc. 707, 2004), transform over TWO axes with `bits` bits — in
+// 3-D too: the reference's hilbert<3> sets n = 2 (vec.h:328) and interleaves axis 2 untransformed.
+__device__ __forceinline__ void skilling2(uint32_t& x0, uint32_t& x1, int bits) {
+  const uint32_t M = 1u << (bits - 1);
+  for (uint32_t Q = M; Q > 1; Q >>= 1) {
+    const uint32_t P = Q - 1;
+    if (x0 & Q) x0 ^= P;  // axis 0: invert (the exchange branch is a no-op for axis 0 with itself)
+    if (x1 & Q) x0 ^= P;  // axis 1: invert ...
+    else {                // ... or exchange low bits of axis 0 and 1
+      const uint32_t t = (x0 ^ x1) & P;
+      x0 ^= t;
+      x1 ^= t;
+    }
+  }
+  x1 ^= x0;  // Gray encode
+  uint32_t t = 0;
+  for (uint32_t Q = M; Q > 1; Q >>= 1)
+    if (x1 & Q) t ^= Q - 1;
+  x0 ^= t;
+  x1 ^= t;
+}
+__device__ __forceinline__ uint64_t spread2(uint64_t x) {  // vec.h:268-275
+  x = (x | x << 16) & 0xffff0000ffffull;
+  x = (x | x << 8) & 0xff00ff00ff00ffull;
+  x = (x | x << 4) & 0xf0f0f0f0f0f0f0full;
+  x = (x | x << 2) & 0x3333333333333333ull;
+  x = (x | x << 1) & 0x5555555555555555ull;
+  return x;
+}
+__device__ __forceinline__ uint64_t spread3(uint64_t x) {  // vec.h:278-286
+  x &= 0x1fffffull;
+  x = (x | x << 32) & 0x1f00000000ffffull;
+  x = (x | x << 16) & 0x1f0000ff0000ffull;
+  x = (x | x << 8) & 0x100f00f00f00f00full;
+  x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+
+template <typename T, int D>
+__global__ void __launch_bounds__(256) hilbert_keys_kernel(const vec4_t<T>* __restrict__ xm, uint32_t n,
+                                                           const Box<T>* __restrict__ box, uint64_t* __restrict__ keys) {
+  uint32_t i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  vec4_t<T> b = xm[i];
+  // bvh.h:42: cast<uint32_t>((x - mins) / grid_cell_size), IEEE subtract + divide, truncating (saturating) convert
+  uint32_t c0 = to_u32_sat(div_rn(sub_rn(b.x, box->lo[0]), box->cell[0]));
+  uint32_t c1 = to_u32_sat(div_rn(sub_rn(b.y, box->lo[1]), box->cell[1]));
+  if (D == 2) {
+    skilling2(c0, c1, 32);
+    keys[i] = spread2(c1) | (spread2(c0) << 1);  // vec.h:277
+  } else {
+    uint32_t c2 = to_u32_sat(div_rn(sub_rn(b.z, box->lo[2]), box->cell[2]));
+    skilling2(c0, c1, 21);
+    keys[i] = spread3(c2) | (spread3(c1) << 1) | (spread3(c0) << 2);  // vec.h:288
+  }
+}
+
+// ---- K13 apply the permutation to all five arrays (bvh.h:71-91) ---------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) gather_kernel(const uint32_t* __restrict__ perm, uint32_t n,
+                                                     const vec4_t<T>* __restrict__ xm_in, vec4_t<T>* __restrict__ xm_out,
+                                                     const vec4_t<T>* __restrict__ v_in, vec4_t<T>* __restrict__ v_out,
+                                                     const vec4_t<T>* __restrict__ a_in, vec4_t<T>* __restrict__ a_out,
+                                                     const vec4_t<T>* __restrict__ ao_in, vec4_t<T>* __restrict__ ao_out) {
+  uint32_t i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  uint32_t src = perm[i];
+  xm_out[i] = xm_in[src];
+  v_out[i]  = v_in[src];
+  a_out[i]  = a_in[src];
+  ao_out[i] = ao_in[src];
+}
+
+// ---- K14/K15 build ----------------------------------------------------------------------------------------------
+template <typename T, int D>
+__device__ __forceinline__ T node_width(vec4_t<T> lo, vec4_t<T> hi) {  // bvh.h:140-144
+  T l0 = sub_rn(hi.x, lo.x), l1 = sub_rn(hi.y, lo.y);
+  T w  = l0 < l1 ? l1 : l0;
+  if (D == 3) {
+    T l2 = sub_rn(hi.z, lo.z);
+    w    = w < l2 ? l2 : w;
+  }
+  return w;
+}
+
+// deepest tree level from pairs of bodies (bvh.h:178-207)
+template <typename T, int D>
+__global__ void __launch_bounds__(256) build_leaf_level_kernel(const vec4_t<T>* __restrict__ xm, uint32_t n, uint32_t first,
+                                                               uint32_t count, vec4_t<T>* node_m, T* bw, vec4_t<T>* lo,
+                                                               vec4_t<T>* hi) {
+  uint32_t li = blockIdx.x * 256 + threadIdx.x;
+  if (li >= count) return;
+  const uint32_t i = first + li, bl = li * 2, br = bl + 1;
+  const T tol = aabb_tol<T>();
+  if (bl >= n) {
+    node_m[i] = make_v4<T>(0, 0, 0, 0);  // dead node (mass 0); b/bw stay as allocated (zero)
+    return;
+  }
+  vec4_t<T> pl = xm[bl];
+  if (br >= n) {
+    node_m[i]     = pl;
+    vec4_t<T> blo = make_v4<T>(sub_rn(pl.x, tol), sub_rn(pl.y, tol), D == 3 ? sub_rn(pl.z, tol) : T(0), 0);
+    vec4_t<T> bhi = make_v4<T>(add_rn(pl.x, tol), add_rn(pl.y, tol), D == 3 ? add_rn(pl.z, tol) : T(0), 0);
+    lo[i] = blo; hi[i] = bhi;
+    bw[i] = node_width<T, D>(blo, bhi);
+    return;
+  }
+  vec4_t<T> pr = xm[br];
+  T mass       = add_rn(pl.w, pr.w);
+  vec4_t<T> c;
+  c.x = div_rn(add_rn(mul_rn(pl.w, pl.x), mul_rn(pr.w, pr.x)), mass);
+  c.y = div_rn(add_rn(mul_rn(pl.w, pl.y), mul_rn(pr.w, pr.y)), mass);
+  c.z = D == 3 ? div_rn(add_rn(mul_rn(pl.w, pl.z), mul_rn(pr.w, pr.z)), mass) : T(0);
+  c.w = mass;
+  node_m[i]     = c;
+  vec4_t<T> blo = make_v4<T>(sub_rn(tmin(pl.x, pr.x), tol), sub_rn(tmin(pl.y, pr.y), tol),
+                             D == 3 ? sub_rn(tmin(pl.z, pr.z), tol) : T(0), 0);
+  vec4_t<T> bhi = make_v4<T>(add_rn(tmax(pl.x, pr.x), tol), add_rn(tmax(pl.y, pr.y), tol),
+                             D == 3 ? add_rn(tmax(pl.z, pr.z), tol) : T(0), 0);
+  lo[i] = blo; hi[i] = bhi;
+  bw[i] = node_width<T, D>(blo, bhi);
+}
+
+// one upper level from its children (bvh.h:210-243)
+template <typename T, int D>
+__global__ void __launch_bounds__(256) build_level_kernel(uint32_t first, uint32_t count, vec4_t<T>* node_m, T* bw,
+                                                          vec4_t<T>* lo, vec4_t<T>* hi) {
+  uint32_t li = blockIdx.x * 256 + threadIdx.x;
+  if (li >= count) return;
+  const uint32_t i = first + li, bl = li * 2 + first + count, br = bl + 1;
+  vec4_t<T> ml = node_m[bl], mr = node_m[br];
+  if (!(ml.w != T(0))) {
+    node_m[i] = ml;
+    return;
+  }
+  if (!(mr.w != T(0))) {
+    node_m[i] = ml;
+    lo[i] = lo[bl]; hi[i] = hi[bl];
+    bw[i] = bw[bl];
+    return;
+  }
+  T mass = add_rn(ml.w, mr.w);
+  vec4_t<T> c;
+  c.x = div_rn(add_rn(mul_rn(ml.w, ml.x), mul_rn(mr.w, mr.x)), mass);
+  c.y = div_rn(add_rn(mul_rn(ml.w, ml.y), mul_rn(mr.w, mr.y)), mass);
+  c.z = D == 3 ? div_rn(add_rn(mul_rn(ml.w, ml.z), mul_rn(mr.w, mr.z)), mass) : T(0);
+  c.w = mass;
+  node_m[i] = c;
+  vec4_t<T> l0 = lo[bl], l1 = lo[br], h0 = hi[bl], h1 = hi[br];
+  vec4_t<T> blo = make_v4<T>(tmin(l0.x, l1.x), tmin(l0.y, l1.y), D == 3 ? tmin(l0.z, l1.z) : T(0), 0);
+  vec4_t<T> bhi = make_v4<T>(tmax(h0.x, h1.x), tmax(h0.y, h1.y), D == 3 ? tmax(h0.z, h1.z) : T(0), 0);
+  lo[i] = blo; hi[i] = bhi;
+  bw[i] = node_width<T, D>(blo, bhi);
+}
+
+// ---- K16 traversal ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float inv_dist3_fast(float d2) {
+  float sq, inv;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(d2));
+  float den = fmaf(d2, sq, FLT_EPSILON);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(den));
+  return inv;
+}
+__device__ __forceinline__ double inv_dist3_fast(double d2) { return 1.0 / fma(d2, sqrt(d2), DBL_EPSILON); }
+
+// dist2 in the reference's order: ((dx*dx) + dy*dy) + dz*dz with d = xs - xj, no contraction (vec.h:232-240)
+template <typename T, int D>
+__device__ __forceinline__ T dist2_exact(T ax, T ay, T az, T bx, T by, T bz) {
+  T dx = sub_rn(ax, bx), dy = sub_rn(ay, by);
+  T r  = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
+  if (D == 3) {
+    T dz = sub_rn(az, bz);
+    r    = add_rn(r, mul_rn(dz, dz));
+  }
+  return r;
+}
+
+// One thread per (Hilbert-sorted) body, the reference's stackless walk over the implicit complete binary tree in heap
+// order (root 0, children 2k+1 / 2k+2): "ascend right" of a left child k is k+1, of a right child k is k/2 one level up
+// (= parent+1, bvh.h:272-281), leaving the body level goes to (k+1)/2. Neighbouring lanes hold neighbouring bodies of
+// the Hilbert order and follow nearly the same path, so node loads are mostly warp-uniform broadcasts.
+template <typename T, int D>
+__global__ void __launch_bounds__(128) bvh_force_kernel(const vec4_t<T>* __restrict__ xm, const vec4_t<T>* __restrict__ node_m,
+                                                        const T* __restrict__ bw, uint32_t n, uint32_t tb, uint32_t te,
+                                                        uint32_t levels, T theta2, T c, vec4_t<T>* __restrict__ a_out) {
+  const uint32_t i = tb + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= te) return;
+  const vec4_t<T> xs     = xm[i];
+  const uint32_t leaf_lv = levels;  // bodies
+  const uint32_t leaf0   = (1u << leaf_lv) - 1;
+  uint32_t k = 0, level = 0;
+  uint64_t covered = 0;
+  T ax = 0, ay = 0, az = 0;
+  while (covered < n) {
+    if (level == leaf_lv) {
+      uint32_t bidx = k - leaf0;
+#pragma unroll
+      for (int q = 0; q < 2; ++q, ++bidx) {
+        if (bidx < n && bidx != i) {
+          vec4_t<T> b = xm[bidx];
+          T d2 = dist2_exact<T, D>(xs.x, xs.y, xs.z, b.x, b.y, b.z);
+          T s  = b.w * inv_dist3_fast(d2);
+          ax = fma(b.x - xs.x, s, ax);
+          ay = fma(b.y - xs.y, s, ay);
+          if (D == 3) az = fma(b.z - xs.z, s, az);
+        }
+      }
+      covered += 2;
+      k = (k + 1) >> 1;
+      level -= 1;
+    } else {
+      const vec4_t<T> nm = node_m[k];
+      const T w          = bw[k];
+      const T d2         = dist2_exact<T, D>(xs.x, xs.y, xs.z, nm.x, nm.y, nm.z);
+      if (mul_rn(w, w) < mul_rn(theta2, d2)) {  // can_approximate (bvh.h:246-248)
+        T s = nm.w * inv_dist3_fast(d2);
+        ax = fma(nm.x - xs.x, s, ax);
+        ay = fma(nm.y - xs.y, s, ay);
+        if (D == 3) az = fma(nm.z - xs.z, s, az);
+        covered += uint64_t(1) << (levels - level);
+        if (k & 1) k += 1;            // left child -> right sibling
+        else { k >>= 1; level -= 1; }  // right child (or root) -> parent + 1, one level up
+      } else {
+        k = 2 * k + 1;
+        level += 1;
+      }
+    }
+  }
+  a_out[i] = make_v4<T>(mul_rn(c, ax), mul_rn(c, ay), D == 3 ? mul_rn(c, az) : T(0), T(0));
+}
+
+// ---- artefact export ---------------------------------------------------------------------------------------------
+template <typename T, int D>
+__global__ void export_nodes_kernel(const vec4_t<T>* node_m, const T* bw, const vec4_t<T>* lo, const vec4_t<T>* hi,
+                                    uint64_t first, uint64_t count, T* out_m, T* out_bw, T* out_b) {
+  uint64_t q = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (q >= count) return;
+  uint64_t i     = first + q;
+  vec4_t<T> m    = node_m[i];
+  T* om          = out_m + q * (D + 1);
+  om[0] = m.x; om[1] = m.y;
+  if (D == 3) om[2] = m.z;
+  om[D]     = m.w;
+  out_bw[q] = bw[i];
+  vec4_t<T> l = lo[i], h = hi[i];
+  T* ob = out_b + q * 2 * D;
+  ob[0] = l.x; ob[1] = l.y;
+  if (D == 3) ob[2] = l.z;
+  ob[D] = h.x; ob[D + 1] = h.y;
+  if (D == 3) ob[D + 2] = h.z;
+}
+
+template <typename T>
+BvhState<T>* st(nbx_engine* e) { return static_cast<BvhState<T>*>(e->bvh); }
+
+}  // namespace
+
+// ---- host side ------------------------------------------------------------------------------------------------------
+template <typename T, int D>
+static int create_impl(nbx_engine* e) {
+  auto* s = new BvhState<T>();
+  e->bvh  = s;
+  uint32_t nleafs = 1, levels = 0;
+  while (nleafs < e->n) { nleafs <<= 1; ++levels; }
+  if (levels > 30) return fail(NBX_ERR_INVALID, "bvh: n too large");
+  s->levels  = levels;
+  s->nnodes  = (uint64_t(1) << levels) - 1;
+  s->nblocks = std::min<uint32_t>((e->n + 255) / 256, uint32_t(e->sm_count) * 8);
+  NBX_CUDA(cudaMalloc(&s->box, sizeof(Box<T>)));
+  NBX_CUDA(cudaMalloc(&s->partial, sizeof(T) * 8 * s->nblocks));
+  NBX_CUDA(cudaMalloc(&s->keys, sizeof(uint64_t) * size_t(e->n)));
+  NBX_CUDA(cudaMalloc(&s->perm, sizeof(uint32_t) * size_t(e->n)));
+  const size_t nn = size_t(s->nnodes ? s->nnodes : 1);
+  NBX_CUDA(cudaMalloc(&s->node_m, sizeof(vec4_t<T>) * nn));
+  NBX_CUDA(cudaMalloc(&s->bw, sizeof(T) * nn));
+  NBX_CUDA(cudaMalloc(&s->lo, sizeof(vec4_t<T>) * nn));
+  NBX_CUDA(cudaMalloc(&s->hi, sizeof(vec4_t<T>) * nn));
+  // the reference never writes b/bw of dead nodes (bvh.h:185-188,225-228): keep them deterministic (zero)
+  NBX_CUDA(cudaMemsetAsync(s->node_m, 0, sizeof(vec4_t<T>) * nn, e->stream));
+  NBX_CUDA(cudaMemsetAsync(s->bw, 0, sizeof(T) * nn, e->stream));
+  NBX_CUDA(cudaMemsetAsync(s->lo, 0, sizeof(vec4_t<T>) * nn, e->stream));
+  NBX_CUDA(cudaMemsetAsync(s->hi, 0, sizeof(vec4_t<T>) * nn, e->stream));
+  const size_t rb = rec_bytes(e);
+  void** alts[3]  = {&e->v_alt, &e->a_alt, &e->ao_alt};
+  for (auto pp : alts) {
+    NBX_CUDA(cudaMalloc(pp, rb * e->n_pad));
+    NBX_CUDA(cudaMemsetAsync(*pp, 0, rb * e->n_pad, e->stream));
+  }
+  NBX_TRY(sorter_create(e, e->n));
+  return NBX_OK;
+}
+
+template <typename T, int D>
+static void destroy_impl(nbx_engine* e) {
+  auto* s = st<T>(e);
+  if (!s) return;
+  void* bufs[] = {s->box, s->partial, s->keys, s->perm, s->node_m, s->bw, s->lo, s->hi};
+  for (void* b : bufs)
+    if (b) cudaFree(b);
+  delete s;
+  e->bvh = nullptr;
+}
+
+template <typename T, int D>
+static int bbox_impl(nbx_engine* e) {
+  auto* s = st<T>(e);
+  bbox_partial_kernel<T, D><<<s->nblocks, 256, 0, e->stream>>>(static_cast<const vec4_t<T>*>(e->xm[e->cur]), e->n, s->partial);
+  bbox_final_kernel<T, D><<<1, 32, 0, e->stream>>>(s->partial, s->nblocks, s->box);
+  e->launches += 2;
+  NBX_CUDA(cudaGetLastError());
+  s->have_box = true;
+  return NBX_OK;
+}
+
+template <typename T, int D>
+static int sort_impl(nbx_engine* e) {
+  auto* s = st<T>(e);
+  if (!s->have_box) return fail(NBX_ERR_STATE, "hilbert_sort before bounding_box");
+  const uint32_t n = e->n;
+  hilbert_keys_kernel<T, D><<<(n + 255) / 256, 256, 0, e->stream>>>(static_cast<const vec4_t<T>*>(e->xm[e->cur]), n, s->box, s->keys);
+  e->launches++;
+  NBX_TRY(sort_pairs(e, s->keys, n, D == 2 ? 64 : 63, s->perm, nullptr));
+  gather_kernel<T><<<(n + 255) / 256, 256, 0, e->stream>>>(
+      s->perm, n, static_cast<const vec4_t<T>*>(e->xm[e->cur]), static_cast<vec4_t<T>*>(e->xm[e->cur ^ 1]),
+      static_cast<const vec4_t<T>*>(e->v), static_cast<vec4_t<T>*>(e->v_alt), static_cast<const vec4_t<T>*>(e->a),
+      static_cast<vec4_t<T>*>(e->a_alt), static_cast<const vec4_t<T>*>(e->ao), static_cast<vec4_t<T>*>(e->ao_alt));
+  e->launches++;
+  NBX_CUDA(cudaGetLastError());
+  e->cur ^= 1;
+  std::swap(e->v, e->v_alt);
+  std::swap(e->a, e->a_alt);
+  std::swap(e->ao, e->ao_alt);
+  s->sorted = true;
+  return NBX_OK;
+}
+
+template <typename T, int D>
+static int build_impl(nbx_engine* e) {
+  auto* s = st<T>(e);
+  if (s->levels == 0) return NBX_OK;
+  const vec4_t<T>* xm = static_cast<const vec4_t<T>*>(e->xm[e->cur]);
+  const uint32_t last = s->levels - 1;
+  {
+    uint32_t first = (1u << last) - 1, count = 1u << last;
+    build_leaf_level_kernel<T, D><<<(count + 255) / 256, 256, 0, e->stream>>>(xm, e->n, first, count, s->node_m, s->bw, s->lo, s->hi);
+    e->launches++;
+  }
+  for (int l = int(last) - 1; l >= 0; --l) {
+    uint32_t first = (1u << l) - 1, count = 1u << l;
+    build_level_kernel<T, D><<<(count + 255) / 256, 256, 0, e->stream>>>(first, count, s->node_m, s->bw, s->lo, s->hi);
+    e->launches++;
+  }
+  NBX_CUDA(cudaGetLastError());
+  s->built = true;
+  return NBX_OK;
+}
+
+template <typename T, int D>
+static int force_impl(nbx_engine* e) {
+  auto* s = st<T>(e);
+  if (!s->built) return fail(NBX_ERR_STATE, "bvh compute_force before build_tree");
+  const uint32_t nt = e->te - e->tb;
+  if (nt == 0) return NBX_OK;
+  const T theta = T(e->cfg.theta);
+  bvh_force_kernel<T, D><<<(nt + 127) / 128, 128, 0, e->stream>>>(static_cast<const vec4_t<T>*>(e->xm[e->cur]), s->node_m, s->bw, e->n,
+                                                                 e->tb, e->te, s->levels, theta * theta, T(e->cfg.G),
+                                                                 static_cast<vec4_t<T>*>(e->a));
+  e->launches++;
+  NBX_CUDA(cudaGetLastError());
+  return NBX_OK;
+}
+
+template <typename T, int D>
+static int get_bbox_impl(nbx_engine* e, void* xmin, void* xmax) {
+  auto* s = st<T>(e);
+  Box<T> h;
+  NBX_CUDA(cudaMemcpyAsync(&h, s->box, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
+  NBX_CUDA(cudaStreamSynchronize(e->stream));
+  e->d2h += sizeof(h);
+  for (int k = 0; k < D; ++k) {
+    if (xmin) static_cast<T*>(xmin)[k] = h.lo[k];
+    if (xmax) static_cast<T*>(xmax)[k] = h.hi[k];
+  }
+  return NBX_OK;
+}
+
+template <typename T, int D>
+static int get_keys_impl(nbx_engine* e, uint64_t* keys, uint32_t* perm) {
+  auto* s = st<T>(e);
+  if (!s->sorted) return fail(NBX_ERR_STATE, "no hilbert_sort has run yet");
+  if (keys) NBX_CUDA(cudaMemcpyAsync(keys, s->keys, sizeof(uint64_t) * size_t(e->n), cudaMemcpyDeviceToHost, e->stream));
+  if (perm) NBX_CUDA(cudaMemcpyAsync(perm, s->perm, sizeof(uint32_t) * size_t(e->n), cudaMemcpyDeviceToHost, e->stream));
+  NBX_CUDA(cudaStreamSynchronize(e->stream));
+  e->d2h += (keys ? 8 : 0) * size_t(e->n) + (perm ? 4 : 0) * size_t(e->n);
+  return NBX_OK;
+}
+
+template <typename T, int D>
+static int get_nodes_impl(nbx_engine* e, uint64_t* nnodes, void* node_m, void* bw, void* b) {
+  auto* s = st<T>(e);
+  if (nnodes) *nnodes = s->nnodes;
+  if (!node_m && !bw && !b) return NBX_OK;
+  if (!node_m || !bw || !b) return fail(NBX_ERR_INVALID, "bvh_get_nodes: pass all three arrays or none");
+  if (!s->built) return fail(NBX_ERR_STATE, "no build_tree has run yet");
+  const uint64_t CH = 1u << 20;  // export in chunks through a bounded staging buffer
+  T *dm = nullptr, *dw = nullptr, *db = nullptr;
+  NBX_CUDA(cudaMalloc(&dm, sizeof(T) * CH * (D + 1)));
+  NBX_CUDA(cudaMalloc(&dw, sizeof(T) * CH));
+  NBX_CUDA(cudaMalloc(&db, sizeof(T) * CH * 2 * D));
+  int rc = NBX_OK;
+  for (uint64_t first = 0; first < s->nnodes && rc == NBX_OK; first += CH) {
+    uint64_t cnt = std::min<uint64_t>(CH, s->nnodes - first);
+    export_nodes_kernel<T, D><<<unsigned((cnt + 255) / 256), 256, 0, e->stream>>>(s->node_m, s->bw, s->lo, s->hi, first, cnt, dm, dw, db);
+    e->launches++;
+    cudaError_t err = cudaMemcpyAsync(static_cast<T*>(node_m) + first * (D + 1), dm, sizeof(T) * cnt * (D + 1), cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(static_cast<T*>(bw) + first, dw, sizeof(T) * cnt, cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(static_cast<T*>(b) + first * 2 * D, db, sizeof(T) * cnt * 2 * D, cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    if (err != cudaSuccess) rc = fail(NBX_ERR_CUDA, cudaGetErrorString(err));
+    e->d2h += sizeof(T) * cnt * (3 * D + 2);
+  }
+  cudaFree(dm); cudaFree(dw); cudaFree(db);
+  return rc;
+}
+
+#define BVH_DISPATCH(e, fn, ...)                                                          \
+  ((e)->prec == 4 ? ((e)->dim == 2 ? fn<float, 2>(__VA_ARGS__) : fn<float, 3>(__VA_ARGS__)) \
+                  : ((e)->dim == 2 ? fn<double, 2>(__VA_ARGS__) : fn<double, 3>(__VA_ARGS__)))
+
+int bvh_create(nbx_engine* e) { return BVH_DISPATCH(e, create_impl, e); }
+void bvh_destroy(nbx_engine* e) {
+  if (!e->bvh) return;
+  BVH_DISPATCH(e, destroy_impl, e);
+}
+int bvh_bounding_box(nbx_engine* e) {
+  PhaseTimer pt(e, PH_BBOX);
+  return BVH_DISPATCH(e, bbox_impl, e);
+}
+int bvh_hilbert_sort(nbx_engine* e) {
+  PhaseTimer pt(e, PH_SORT);
+  return BVH_DISPATCH(e, sort_impl, e);
+}
+int bvh_build_tree(nbx_engine* e) {
+  PhaseTimer pt(e, PH_MONO);
+  return BVH_DISPATCH(e, build_impl, e);
+}
+int bvh_compute_force(nbx_engine* e) {
+  PhaseTimer pt(e, PH_TRAVERSE);
+  return BVH_DISPATCH(e, force_impl, e);
+}
+int bvh_get_bbox(nbx_engine* e, void* xmin, void* xmax) { return BVH_DISPATCH(e, get_bbox_impl, e, xmin, xmax); }
+int bvh_get_keys(nbx_engine* e, uint64_t* keys, uint32_t* perm) { return BVH_DISPATCH(e, get_keys_impl, e, keys, perm); }
+int bvh_get_nodes(nbx_engine* e, uint64_t* nnodes, void* node_m, void* bw, void* b) {
+  return BVH_DISPATCH(e, get_nodes_impl, e, nnodes, node_m, bw, b);
+}
+
+}  // namespace nbx

@@ -245,8 +245,8 @@ int nbx_create(const nbx_config* cfg, nbx_engine** out) {
   }
   void** vecs[3] = {&e->v, &e->a, &e->ao};
   for (auto pp : vecs) {
-    NBX_CUDA_B(cudaMalloc(pp, rb * e->n));
-    NBX_CUDA_B(cudaMemsetAsync(*pp, 0, rb * e->n, e->stream));
+    NBX_CUDA_B(cudaMalloc(pp, rb * e->n_pad));
+    NBX_CUDA_B(cudaMemsetAsync(*pp, 0, rb * e->n_pad, e->stream));
   }
   int rc = NBX_OK;
   if (e->algo == NBX_BVH) rc = bvh_create(e);

@@ -51,8 +51,7 @@ def test_force_vs_oracle(oracle, oracle_fast, tag, dim, n):
     dt = DT[tag]
     s = oracle.galaxy(n, dt, dim)
     out = run_force(s)
-    s64 = as64(s)
-    truth = oracle_fast.all_pairs_force(s64["m"], s64["x"], s64["G"])       # double oracle on the same inputs
+    truth = oracle_fast.all_pairs_force_truth(s["m"], s["x"], s["G"])  # double arithmetic, eps of this precision
     err = rel_err(out["a"], truth)
     tol_rms, tol_max = TOL_A[np.dtype(dt)]
     assert rms(err) <= tol_rms and err.max() <= tol_max, (rms(err), err.max())
@@ -162,8 +161,7 @@ def test_full_size_properties_1M(oracle_fast):
     assert np.isfinite(out["a"]).all()
     rng = np.random.default_rng(0)
     targets = np.sort(rng.choice(n, 48, replace=False)).astype(np.uint32)
-    s64 = as64(s)
-    truth = oracle_fast.all_pairs_force(s64["m"], s64["x"], s64["G"], targets=targets)
+    truth = oracle_fast.all_pairs_force_truth(s["m"], s["x"], s["G"], targets=targets)
     err = rel_err(out["a"][targets], truth)
     assert rms(err) <= 5e-5 and err.max() <= 5e-4, (rms(err), err.max())
     ref32 = oracle_fast.all_pairs_force(s["m"], s["x"], s["G"], targets=targets)
