@@ -589,19 +589,26 @@ int all_pairs_collapsed_force(nbx_engine* e) {
 }
 
 template <typename T, int D>
-static int launch_accelerate(nbx_engine* e) {
-  const uint32_t nt = e->te - e->tb;
+static int launch_accelerate(nbx_engine* e, uint32_t tb, uint32_t te) {
+  const uint32_t nt = te - tb;
   if (nt == 0) return NBX_OK;
-  accelerate_kernel<T, D><<<(nt + 255) / 256, 256, 0, e->stream>>>(make_leap<T>(e, /*to_next=*/false), e->tb, e->te);
+  accelerate_kernel<T, D><<<(nt + 255) / 256, 256, 0, e->stream>>>(make_leap<T>(e, /*to_next=*/false), tb, te);
   e->launches++;
   NBX_CUDA(cudaGetLastError());
   return NBX_OK;
 }
 
-int accelerate_step(nbx_engine* e) {
+int accelerate_range(nbx_engine* e, uint32_t tb, uint32_t te) {
   PhaseTimer pt(e, PH_ACCEL);
-  if (e->prec == 4) return e->dim == 2 ? launch_accelerate<float, 2>(e) : launch_accelerate<float, 3>(e);
-  return e->dim == 2 ? launch_accelerate<double, 2>(e) : launch_accelerate<double, 3>(e);
+  if (e->prec == 4) return e->dim == 2 ? launch_accelerate<float, 2>(e, tb, te) : launch_accelerate<float, 3>(e, tb, te);
+  return e->dim == 2 ? launch_accelerate<double, 2>(e, tb, te) : launch_accelerate<double, 3>(e, tb, te);
+}
+
+// Trees keep the whole state replicated on every rank (accelerations are all-gathered), so they integrate all bodies;
+// the all-pairs variants integrate their own targets and all-gather the new positions.
+int accelerate_step(nbx_engine* e) {
+  const bool tree = e->algo == NBX_BVH || e->algo == NBX_OCTREE;
+  return tree ? accelerate_range(e, 0, e->n) : accelerate_range(e, e->tb, e->te);
 }
 
 template <typename T, int D>

@@ -75,11 +75,14 @@ int comm_init_rank(nbx_engine* e, const void* id128) {
   return NBX_OK;
 }
 
-int comm_allgather_positions(nbx_engine* e) {
+int comm_allgather_positions(nbx_engine* e) { return comm_allgather(e, e->xm[e->cur]); }
+
+// in-place all-gather of one vec4 array: rank r contributes records [r*chunk, (r+1)*chunk)
+int comm_allgather(nbx_engine* e, void* vec4_array) {
   if (e->cfg.world_size <= 1) return NBX_OK;
   if (!e->comm) return fail(NBX_ERR_COMM, "multi-GPU engine used before nbx_comm_init_rank");
   PhaseTimer pt(e, PH_COMM);
-  char* base         = static_cast<char*>(e->xm[e->cur]);
+  char* base         = static_cast<char*>(vec4_array);
   const size_t bytes = rec_bytes(e) * e->chunk;
   ncclResult_t r = api().AllGather(base + bytes * e->cfg.rank, base, bytes, ncclChar, (ncclComm_t)e->comm, e->stream);
   if (r != 0) return nccl_fail("ncclAllGather", r);

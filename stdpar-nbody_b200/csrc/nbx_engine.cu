@@ -152,13 +152,14 @@ static int one_step(nbx_engine* e) {
       NBX_TRY(bvh_hilbert_sort(e));
       NBX_TRY(bvh_build_tree(e));
       NBX_TRY(bvh_compute_force(e));
+      if (multi) NBX_TRY(comm_allgather(e, e->a));  // a[tb,te) of every rank -> full a everywhere
       NBX_TRY(accelerate_step(e));
-      break;
+      return NBX_OK;
     case NBX_OCTREE:
       NBX_TRY(octree_build(e));
-      NBX_TRY(octree_compute_force(e));
+      NBX_TRY(octree_compute_force(e));  // all-gathers the sorted-slot accelerations itself
       NBX_TRY(accelerate_step(e));
-      break;
+      return NBX_OK;
     default: return fail(NBX_ERR_INVALID, "unknown algorithm");
   }
   if (multi) NBX_TRY(comm_allgather_positions(e));
@@ -297,6 +298,7 @@ int nbx_download(nbx_engine* e, void* m, void* x, void* v, void* a, void* ao) {
 int nbx_step(nbx_engine* e, uint32_t steps) {
   NBX_ENTER(e);
   for (uint32_t s = 0; s < steps; ++s) NBX_TRY(one_step(e));
+  if (e->algo == NBX_OCTREE && steps) NBX_TRY(octree_check(e));
   return NBX_OK;
 }
 
@@ -308,6 +310,7 @@ int nbx_step_timed(nbx_engine* e, uint32_t steps, float* ms) {
   NBX_CUDA(cudaEventSynchronize(e->ev1));
   if (ms) NBX_CUDA(cudaEventElapsedTime(ms, e->ev0, e->ev1));
   collect_phase_times(e);
+  if (e->algo == NBX_OCTREE && steps) NBX_TRY(octree_check(e));
   return NBX_OK;
 }
 
@@ -371,7 +374,8 @@ int nbx_bvh_get_nodes(nbx_engine* e, uint64_t* nnodes, void* node_m, void* bw, v
 int nbx_octree_build(nbx_engine* e) {
   NBX_ENTER(e);
   if (e->algo != NBX_OCTREE) return fail(NBX_ERR_STATE, "engine was not created with NBX_OCTREE");
-  return octree_build(e);
+  NBX_TRY(octree_build(e));
+  return octree_check(e);
 }
 int nbx_octree_compute_force(nbx_engine* e) {
   NBX_ENTER(e);

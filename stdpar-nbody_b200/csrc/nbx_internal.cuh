@@ -127,7 +127,8 @@ inline size_t rec_bytes(const nbx_engine* e) { return size_t(4) * e->prec; }
 // nbx_allpairs.cu
 int all_pairs_force(nbx_engine* e, bool fuse_integrate);
 int all_pairs_collapsed_force(nbx_engine* e);
-int accelerate_step(nbx_engine* e);
+int accelerate_step(nbx_engine* e);                               // over this rank's targets [tb, te)
+int accelerate_range(nbx_engine* e, uint32_t begin, uint32_t end);  // over [begin, end)
 int calc_energies(nbx_engine* e, double* kinetic, double* grav);
 int measure_fma_peak(int device, int precision, double* tflops);
 // nbx_sort.cu : stable LSD radix sort of (u64 key, u32 value) pairs
@@ -152,6 +153,7 @@ int octree_create(nbx_engine* e);
 void octree_destroy(nbx_engine* e);
 int octree_build(nbx_engine* e);
 int octree_compute_force(nbx_engine* e);
+int octree_check(nbx_engine* e);  // NBX_ERR_CAPACITY if the last build overflowed (syncs the stream)
 int octree_get_root(nbx_engine* e, void* side, void* root_x, uint64_t* nodes_used);
 int octree_get_canonical(nbx_engine* e, uint64_t* count, uint32_t* depth, uint64_t* path, uint32_t* kind,
                          void* monopole);
@@ -159,6 +161,7 @@ int octree_get_canonical(nbx_engine* e, uint64_t* count, uint32_t* depth, uint64
 int comm_unique_id(void* id128);
 int comm_init_rank(nbx_engine* e, const void* id128);
 int comm_allgather_positions(nbx_engine* e);  // all-gather xm[cur] shards (chunk records per rank), in place
+int comm_allgather(nbx_engine* e, void* vec4_array);
 void comm_destroy(nbx_engine* e);
 
 }  // namespace nbx

@@ -1,0 +1,593 @@
+// nbx_octree.cu — Barnes-Hut octree (quadtree in 2-D) for sm_100a, built by sorting instead of by locks.
+//
+// The reference builds the tree with a CAS-locked concurrent insert and a bump allocator (src/octree.h:115-181), then
+// climbs from every leaf with an acq_rel latch (src/octree.h:184-224) and walks it stacklessly through parent links
+// (src/octree.h:63-71,227-255). Node numbering there depends on the thread schedule; the SET of cells, the child order
+// and every monopole do not. This file produces that same set of cells deterministically:
+//
+//   bounds kernels     : octree::compute_bounds (src/octree.h:93-112)                                   [K6]
+//   path_keys_kernel   : each body replays the descent arithmetic of octree::insert (src/octree.h:126-138) on its own —
+//                        child bit d = pos[d] > divide[d], divide[d] += (+-1)*side/4, side /= 2 — in the reference's
+//                        exact floating-point order, giving a D-bit digit per level, root first                [K7]
+//   sort_pairs         : radix sort of the path keys (nbx_sort.cu); sorted order == DFS order of the leaves
+//   cells kernels      : a cell of depth d exists iff two adjacent sorted bodies share d digits; cells are emitted in
+//                        DFS pre-order into ONE linear array together with the body leaves ("records")     [K5/K7]
+//   monopole kernels   : children summed in child order 0..2^D-1, deepest level first (src/octree.h:205-216)   [K8]
+//   force_kernel       : walk over the pre-order array: accept -> jump to `next` (end of subtree), open -> p+1 [K9]
+//
+// Empty children are not stored: in the reference they contribute m=0 at x=0, i.e. exactly +0 to every sum.
+// Record = monopole (x,y,z,m) + {next, depth|leaf<<8}: 24 B (float) / 40 B (double), read strictly front to back.
+#include <cfloat>
+
+#include "nbx_internal.cuh"
+
+namespace nbx {
+
+namespace {
+
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+
+template <int D>
+struct KeyTraits {
+  static constexpr int MAXL = D == 3 ? 21 : 32;  // levels that fit a 64-bit key
+  static constexpr int BITS = D * MAXL;          // 63 / 64
+};
+
+constexpr uint32_t LEAF_FLAG = 0x100u;
+
+template <typename T>
+struct Root {
+  T side;
+  T x;          // root_x = splat(divide)
+  uint32_t cells;     // internal cells of the last build
+  uint32_t overflow;  // 1: bodies not separated within MAXL levels, or more cells than capacity
+};
+
+template <typename T>
+struct OctreeState {
+  Root<T>* root      = nullptr;
+  T* partial         = nullptr;  // [blocks][2]
+  uint32_t nblocks   = 0;
+  uint64_t* keys     = nullptr;  // path keys, entry order
+  uint64_t* skeys    = nullptr;  // sorted
+  uint32_t* perm     = nullptr;  // sorted slot -> body id
+  uint32_t* delta    = nullptr;  // [n] common-prefix levels of sorted neighbours s, s+1 (MAXL+1.. see kernel)
+  uint32_t* cnt      = nullptr;  // [n+1] cells starting at sorted body s -> exclusive scan in place (cell_base)
+  uint32_t* blocksum = nullptr;
+  uint32_t cap       = 0;        // record capacity = 2n + 1
+  vec4_t<T>* mono    = nullptr;  // [cap]
+  uint2* meta        = nullptr;  // [cap] {next, depth | leaf<<8}
+  uint32_t* rec_body = nullptr;  // [cap] first sorted body of the node (for the canonical path code)
+  uint32_t* cell_pos = nullptr;  // [n] record index of internal cell c
+  vec4_t<T>* a_sorted = nullptr; // [n_pad] accelerations in sorted-slot order
+  bool built = false;
+};
+
+// ---- K6 bounds (octree.h:93-112): scalar min/max over every coordinate, identity 0 --------------------------------
+template <typename T, int D>
+__global__ void __launch_bounds__(256) bounds_partial_kernel(const vec4_t<T>* __restrict__ xm, uint32_t n, T* partial) {
+  T lo = 0, hi = 0;
+  for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    vec4_t<T> b = xm[i];
+    T mn = fmin(b.x, b.y), mx = fmax(b.x, b.y);
+    if (D == 3) { mn = fmin(mn, b.z); mx = fmax(mx, b.z); }
+    lo = fmin(lo, mn);
+    hi = fmax(hi, mx);
+  }
+  __shared__ T red[8][2];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+  }
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = lo; red[threadIdx.x >> 5][1] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { lo = fmin(lo, red[w][0]); hi = fmax(hi, red[w][1]); }
+    partial[blockIdx.x * 2]     = lo;
+    partial[blockIdx.x * 2 + 1] = hi;
+  }
+}
+
+template <typename T>
+__global__ void bounds_final_kernel(const T* partial, uint32_t nblocks, Root<T>* root) {
+  if (threadIdx.x != 0) return;
+  T lo = 0, hi = 0;
+  for (uint32_t b = 0; b < nblocks; ++b) { lo = fmin(lo, partial[2 * b]); hi = fmax(hi, partial[2 * b + 1]); }
+  hi = add_rn(hi, T(1));                          // max_size += 1
+  lo = sub_rn(lo, T(1));                          // min_size -= 1
+  root->x        = div_rn(add_rn(hi, lo), T(2));  // divide
+  root->side     = sub_rn(hi, lo);
+  root->overflow = 0;
+  root->cells    = 0;
+}
+
+// ---- K7 path keys -------------------------------------------------------------------------------------------------
+template <typename T, int D>
+__global__ void __launch_bounds__(256) path_keys_kernel(const vec4_t<T>* __restrict__ xm, uint32_t n,
+                                                        const Root<T>* __restrict__ root, uint64_t* __restrict__ keys) {
+  uint32_t i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  vec4_t<T> b = xm[i];
+  const T pos[3] = {b.x, b.y, b.z};
+  T divide[3]    = {root->x, root->x, root->x};
+  T side         = root->side;
+  uint64_t key   = 0;
+#pragma unroll 1
+  for (int level = 0; level < KeyTraits<D>::MAXL; ++level) {
+    const T half = div_rn(side, T(4));  // "/4: /2 for the new side, /2 for half of it" (octree.h:126-127)
+    uint32_t cp  = 0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const bool gt = pos[k] > divide[k];
+      cp |= uint32_t(gt) << k;
+      divide[k] = add_rn(divide[k], gt ? half : -half);  // (2*gt - 1) * half
+    }
+    side = div_rn(side, T(2));
+    key  = (key << D) | cp;
+  }
+  keys[i] = key;
+}
+
+// ---- cells --------------------------------------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ uint32_t common_levels(uint64_t a, uint64_t b) {
+  uint64_t x = a ^ b;
+  if (x == 0) return KeyTraits<D>::MAXL;
+  int lead = __clzll((long long)x) - (64 - KeyTraits<D>::BITS);
+  return uint32_t(lead / D);
+}
+
+// delta[s] = levels shared by sorted bodies s and s+1 (s < n-1); cnt[s] = number of cells whose first body is s
+template <int D>
+__global__ void __launch_bounds__(256) delta_kernel(const uint64_t* __restrict__ skeys, uint32_t n, uint32_t* delta,
+                                                    uint32_t* cnt, uint32_t* overflow) {
+  uint32_t s = blockIdx.x * 256 + threadIdx.x;
+  if (s > n) return;
+  if (s == n) { cnt[n] = 0; return; }
+  // shared levels with the next / previous body; "-1" is encoded by computing with +1 offsets
+  uint32_t dn = s + 1 < n ? common_levels<D>(skeys[s], skeys[s + 1]) + 1 : 0;  // delta_s + 1   (0 = none)
+  uint32_t dp = s > 0 ? common_levels<D>(skeys[s - 1], skeys[s]) + 1 : 0;      // delta_{s-1} + 1
+  if (dn == KeyTraits<D>::MAXL + 1) atomicExch(overflow, 1u);                  // coincident within MAXL levels
+  delta[s] = dn;
+  cnt[s]   = dn > dp ? dn - dp : 0;
+}
+
+// generic exclusive scan of u32 (3 kernels), in place; data has `count` entries
+constexpr int SC_TILE = 4096;
+__global__ void __launch_bounds__(1024) scan_reduce_kernel(const uint32_t* data, uint32_t count, uint32_t* blocksum) {
+  __shared__ uint32_t ws[32];
+  uint32_t base = blockIdx.x * SC_TILE, v = 0;
+  for (int k = 0; k < 4; ++k) {
+    uint32_t i = base + k * 1024 + threadIdx.x;
+    if (i < count) v += data[i];
+  }
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = ws[threadIdx.x];
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (threadIdx.x == 0) blocksum[blockIdx.x] = v;
+  }
+}
+__global__ void __launch_bounds__(1024) scan_blocksums_kernel(uint32_t* blocksum, uint32_t nb, uint32_t* total_out) {
+  __shared__ uint32_t ws[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t base = 0; base < nb; base += 1024) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = i < nb ? blocksum[i] : 0, s = v;
+    for (int off = 1; off < 32; off <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, s, off);
+      if (lane >= off) s += t;
+    }
+    if (lane == 31) ws[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = ws[lane];
+      for (int off = 1; off < 32; off <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, w, off);
+        if (lane >= off) w += t;
+      }
+      ws[lane] = w;
+    }
+    __syncthreads();
+    uint32_t ex = carry + (warp ? ws[warp - 1] : 0) + (s - v);
+    if (i < nb) blocksum[i] = ex;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = ex + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+__global__ void __launch_bounds__(1024) scan_apply_kernel(uint32_t* data, uint32_t count, const uint32_t* blocksum) {
+  __shared__ uint32_t ws[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = blocksum[blockIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t base = blockIdx.x * SC_TILE;
+  for (int k = 0; k < 4; ++k) {
+    uint32_t i = base + k * 1024 + threadIdx.x;
+    uint32_t v = i < count ? data[i] : 0, s = v;
+    for (int off = 1; off < 32; off <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, s, off);
+      if (lane >= off) s += t;
+    }
+    if (lane == 31) ws[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = ws[lane];
+      for (int off = 1; off < 32; off <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, w, off);
+        if (lane >= off) w += t;
+      }
+      ws[lane] = w;
+    }
+    __syncthreads();
+    uint32_t ex = carry + (warp ? ws[warp - 1] : 0) + (s - v);
+    if (i < count) data[i] = ex;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = ex + v;
+    __syncthreads();
+  }
+}
+
+// One thread per sorted body s: emits its leaf record and the records of every cell that starts at s.
+// Record index of cell (s, depth d) = s + cell_id, cell_id = cell_base[s] + (d - first depth); of leaf s = s + cell_base[s+1].
+// `next` of a cell = record index right after its last body e: (e + 1) + cell_base[e + 1].
+template <typename T, int D>
+__global__ void __launch_bounds__(256) emit_records_kernel(const uint64_t* __restrict__ skeys, const uint32_t* __restrict__ perm,
+                                                           const vec4_t<T>* __restrict__ xm, uint32_t n,
+                                                           const uint32_t* __restrict__ delta, const uint32_t* __restrict__ cell_base,
+                                                           uint32_t cap, vec4_t<T>* mono, uint2* meta, uint32_t* rec_body,
+                                                           uint32_t* cell_pos, Root<T>* root) {
+  uint32_t s = blockIdx.x * 256 + threadIdx.x;
+  if (s >= n) return;
+  constexpr int MAXL = KeyTraits<D>::MAXL;
+  const uint32_t dn = delta[s];                      // delta_s + 1
+  const uint32_t dp = s > 0 ? delta[s - 1] : 0;      // delta_{s-1} + 1
+  const uint32_t cb = cell_base[s], cb_next = cell_base[s + 1];
+  if (s == n - 1) {
+    root->cells = cb_next;
+    if (cb_next > n) root->overflow = 1;
+  }
+  // leaf: depth = deepest shared level + 1
+  const uint32_t leaf_depth = (dn > dp ? dn : dp);  // max(delta_s, delta_{s-1}) + 1, and 0 for a single body
+  const uint32_t lpos       = s + cb_next;
+  if (lpos < cap) {
+    mono[lpos]     = xm[perm[s]];
+    meta[lpos]     = make_uint2(lpos + 1, leaf_depth | LEAF_FLAG);
+    rec_body[lpos] = s;
+  }
+  if (dn <= dp) return;
+  const uint64_t key = skeys[s];
+  for (uint32_t q = 0; q < dn - dp; ++q) {
+    const uint32_t depth = dp + q;  // cells at depths delta_{s-1}+1 .. delta_s  (dp = delta_{s-1}+1)
+    // last body e sharing `depth` digits with s: binary search on the sorted keys
+    const int shift   = D * (MAXL - int(depth));
+    const uint64_t pf = depth == 0 ? 0 : (shift >= 64 ? 0 : key >> shift);
+    uint32_t lo = s, hi = n - 1;  // invariant: lo shares the prefix
+    while (lo < hi) {
+      uint32_t mid = lo + (hi - lo + 1) / 2;
+      uint64_t pm  = depth == 0 ? 0 : (shift >= 64 ? 0 : skeys[mid] >> shift);
+      if (pm == pf) lo = mid;
+      else hi = mid - 1;
+    }
+    const uint32_t e   = lo;
+    const uint32_t cid = cb + q;
+    const uint32_t pos = s + cid;
+    if (pos < cap && cid < n) {
+      meta[pos]     = make_uint2((e + 1) + cell_base[e + 1], depth);
+      rec_body[pos] = s;
+      cell_pos[cid] = pos;
+    }
+  }
+}
+
+// ---- K8 monopoles: one launch per depth, deepest first (octree.h:205-216: m = sum m_c ; x = sum m_c*x_c / m) -------------
+template <typename T, int D>
+__global__ void __launch_bounds__(256) monopole_level_kernel(const uint32_t* __restrict__ cell_pos, const Root<T>* __restrict__ root,
+                                                             uint32_t depth, uint32_t cap, vec4_t<T>* mono, const uint2* __restrict__ meta) {
+  uint32_t c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= root->cells) return;
+  const uint32_t p = cell_pos[c];
+  if (p >= cap) return;
+  const uint2 me = meta[p];
+  if ((me.y & 0xff) != depth) return;
+  T m = 0, x = 0, y = 0, z = 0;
+  uint32_t q = p + 1;
+  while (q < me.x && q < cap) {  // children in child order
+    const vec4_t<T> cm = mono[q];
+    m = add_rn(m, cm.w);
+    x = add_rn(x, mul_rn(cm.w, cm.x));
+    y = add_rn(y, mul_rn(cm.w, cm.y));
+    if (D == 3) z = add_rn(z, mul_rn(cm.w, cm.z));
+    q = meta[q].x;
+  }
+  mono[p] = make_v4<T>(div_rn(x, m), div_rn(y, m), D == 3 ? div_rn(z, m) : T(0), m);
+}
+
+// ---- K9 traversal ---------------------------------------------------------------------------------------------------
+// octree.h:227-255: dx = sqrt(dist2)+eps ; accept when leaf or side/dx < theta ; a += m*(xj-x)/dx^3.
+template <typename T>
+struct WalkMath;
+template <>
+struct WalkMath<float> {
+  static __device__ __forceinline__ float dist(float d2) {
+    float sq;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(d2));
+    return sq + FLT_EPSILON;
+  }
+  static __device__ __forceinline__ bool accept(float side, float dx, float theta) { return side < theta * dx; }
+  static __device__ __forceinline__ float inv_cube(float dx) {
+    float inv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(dx * dx * dx));
+    return inv;
+  }
+  static __device__ __forceinline__ float side_at(float root_side, uint32_t depth) {
+    return root_side * __int_as_float(int(127 - depth) << 23);  // exact halvings
+  }
+};
+template <>
+struct WalkMath<double> {
+  static __device__ __forceinline__ double dist(double d2) { return sqrt(d2) + DBL_EPSILON; }
+  static __device__ __forceinline__ bool accept(double side, double dx, double theta) { return side / dx < theta; }
+  static __device__ __forceinline__ double inv_cube(double dx) { return 1.0 / (dx * dx * dx); }
+  static __device__ __forceinline__ double side_at(double root_side, uint32_t depth) {
+    return root_side * __longlong_as_double((long long)(1023 - depth) << 52);
+  }
+};
+
+// One thread per SORTED slot t (body perm[t]): neighbouring lanes are neighbours along the tree's DFS order and read the
+// same records most of the time. The result goes to a_sorted[t].
+template <typename T, int D>
+__global__ void __launch_bounds__(128) octree_force_kernel(const vec4_t<T>* __restrict__ mono, const uint2* __restrict__ meta,
+                                                           const Root<T>* __restrict__ root, const uint32_t* __restrict__ cell_base,
+                                                           uint32_t n, uint32_t tb, uint32_t te, T theta, T c,
+                                                           vec4_t<T>* __restrict__ a_sorted) {
+  const uint32_t t = tb + blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= te) return;
+  const uint32_t nrec  = n + root->cells;
+  const T root_side    = root->side;
+  const vec4_t<T> xs   = mono[t + cell_base[t + 1]];  // own leaf record = own position
+  T ax = 0, ay = 0, az = 0;
+  uint32_t p = 0;
+  while (p < nrec) {
+    const vec4_t<T> nm = mono[p];
+    const uint2 me     = meta[p];
+    const T dx_ = nm.x - xs.x, dy_ = nm.y - xs.y, dz_ = D == 3 ? nm.z - xs.z : T(0);
+    T d2 = fma(dy_, dy_, dx_ * dx_);
+    if (D == 3) d2 = fma(dz_, dz_, d2);
+    const T dx = WalkMath<T>::dist(d2);
+    if ((me.y & LEAF_FLAG) || WalkMath<T>::accept(WalkMath<T>::side_at(root_side, me.y & 0xff), dx, theta)) {
+      const T s = nm.w * WalkMath<T>::inv_cube(dx);
+      ax = fma(dx_, s, ax);
+      ay = fma(dy_, s, ay);
+      if (D == 3) az = fma(dz_, s, az);
+      p = me.x;
+    } else {
+      p = p + 1;
+    }
+  }
+  a_sorted[t] = make_v4<T>(c * ax, c * ay, D == 3 ? c * az : T(0), T(0));
+}
+
+// a[perm[t]] = a_sorted[t]
+template <typename T>
+__global__ void __launch_bounds__(256) unsort_kernel(const uint32_t* __restrict__ perm, const vec4_t<T>* __restrict__ a_sorted,
+                                                     uint32_t n, vec4_t<T>* __restrict__ a) {
+  uint32_t t = blockIdx.x * 256 + threadIdx.x;
+  if (t < n) a[perm[t]] = a_sorted[t];
+}
+
+template <typename T, int D>
+__global__ void export_canonical_kernel(const vec4_t<T>* mono, const uint2* meta, const uint32_t* rec_body,
+                                        const uint64_t* skeys, uint32_t nrec, uint32_t* depth, uint64_t* path, uint32_t* kind,
+                                        T* out_m) {
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nrec) return;
+  const uint2 me   = meta[p];
+  const uint32_t d = me.y & 0xff;
+  depth[p]         = d;
+  kind[p]          = (me.y & LEAF_FLAG) ? 1u : 0u;
+  const int shift  = D * (KeyTraits<D>::MAXL - int(d));
+  path[p]          = d == 0 ? 0 : (shift >= 64 ? 0 : skeys[rec_body[p]] >> shift);
+  vec4_t<T> m      = mono[p];
+  T* om            = out_m + size_t(p) * (D + 1);
+  om[0] = m.x; om[1] = m.y;
+  if (D == 3) om[2] = m.z;
+  om[D] = m.w;
+}
+
+template <typename T>
+OctreeState<T>* st(nbx_engine* e) { return static_cast<OctreeState<T>*>(e->octree); }
+
+}  // namespace
+
+template <typename T, int D>
+static int create_impl(nbx_engine* e) {
+  auto* s    = new OctreeState<T>();
+  e->octree  = s;
+  const size_t n = e->n;
+  s->nblocks = std::min<uint32_t>((e->n + 255) / 256, uint32_t(e->sm_count) * 8);
+  s->cap     = uint32_t(std::min<uint64_t>(2 * uint64_t(n) + 1, 0xfffffff0ull));
+  NBX_CUDA(cudaMalloc(&s->root, sizeof(Root<T>)));
+  NBX_CUDA(cudaMemsetAsync(s->root, 0, sizeof(Root<T>), e->stream));
+  NBX_CUDA(cudaMalloc(&s->partial, sizeof(T) * 2 * s->nblocks));
+  NBX_CUDA(cudaMalloc(&s->keys, sizeof(uint64_t) * n));
+  NBX_CUDA(cudaMalloc(&s->skeys, sizeof(uint64_t) * n));
+  NBX_CUDA(cudaMalloc(&s->perm, sizeof(uint32_t) * n));
+  NBX_CUDA(cudaMalloc(&s->delta, sizeof(uint32_t) * n));
+  NBX_CUDA(cudaMalloc(&s->cnt, sizeof(uint32_t) * (n + 1)));
+  NBX_CUDA(cudaMalloc(&s->blocksum, sizeof(uint32_t) * ((n + 1 + SC_TILE - 1) / SC_TILE + 1)));
+  NBX_CUDA(cudaMalloc(&s->mono, sizeof(vec4_t<T>) * s->cap));
+  NBX_CUDA(cudaMalloc(&s->meta, sizeof(uint2) * s->cap));
+  NBX_CUDA(cudaMalloc(&s->rec_body, sizeof(uint32_t) * s->cap));
+  NBX_CUDA(cudaMalloc(&s->cell_pos, sizeof(uint32_t) * n));
+  NBX_CUDA(cudaMalloc(&s->a_sorted, sizeof(vec4_t<T>) * e->n_pad));
+  NBX_CUDA(cudaMemsetAsync(s->a_sorted, 0, sizeof(vec4_t<T>) * e->n_pad, e->stream));
+  NBX_TRY(sorter_create(e, e->n));
+  return NBX_OK;
+}
+
+template <typename T, int D>
+static void destroy_impl(nbx_engine* e) {
+  auto* s = st<T>(e);
+  if (!s) return;
+  void* bufs[] = {s->root, s->partial, s->keys, s->skeys, s->perm, s->delta, s->cnt, s->blocksum,
+                  s->mono, s->meta, s->rec_body, s->cell_pos, s->a_sorted};
+  for (void* b : bufs)
+    if (b) cudaFree(b);
+  delete s;
+  e->octree = nullptr;
+}
+
+template <typename T, int D>
+static int build_impl(nbx_engine* e) {
+  auto* s = st<T>(e);
+  const uint32_t n = e->n;
+  const vec4_t<T>* xm = static_cast<const vec4_t<T>*>(e->xm[e->cur]);
+  const unsigned gb = (n + 255) / 256;
+  {
+    PhaseTimer pt(e, PH_BBOX);
+    bounds_partial_kernel<T, D><<<s->nblocks, 256, 0, e->stream>>>(xm, n, s->partial);
+    bounds_final_kernel<T><<<1, 32, 0, e->stream>>>(s->partial, s->nblocks, s->root);
+    e->launches += 2;
+  }
+  {
+    PhaseTimer pt(e, PH_SORT);
+    path_keys_kernel<T, D><<<gb, 256, 0, e->stream>>>(xm, n, s->root, s->keys);
+    e->launches++;
+    NBX_TRY(sort_pairs(e, s->keys, n, KeyTraits<D>::BITS, s->perm, s->skeys));
+  }
+  {
+    PhaseTimer pt(e, PH_BUILD);
+    delta_kernel<D><<<(n + 1 + 255) / 256, 256, 0, e->stream>>>(s->skeys, n, s->delta, s->cnt, &s->root->overflow);
+    const uint32_t count = n + 1, nb = (count + SC_TILE - 1) / SC_TILE;
+    scan_reduce_kernel<<<nb, 1024, 0, e->stream>>>(s->cnt, count, s->blocksum);
+    scan_blocksums_kernel<<<1, 1024, 0, e->stream>>>(s->blocksum, nb, nullptr);
+    scan_apply_kernel<<<nb, 1024, 0, e->stream>>>(s->cnt, count, s->blocksum);
+    emit_records_kernel<T, D><<<gb, 256, 0, e->stream>>>(s->skeys, s->perm, xm, n, s->delta, s->cnt, s->cap, s->mono, s->meta,
+                                                        s->rec_body, s->cell_pos, s->root);
+    e->launches += 5;
+  }
+  {
+    PhaseTimer pt(e, PH_MONO);
+    for (int depth = KeyTraits<D>::MAXL - 1; depth >= 0; --depth) {
+      monopole_level_kernel<T, D><<<gb, 256, 0, e->stream>>>(s->cell_pos, s->root, uint32_t(depth), s->cap, s->mono, s->meta);
+      e->launches++;
+    }
+  }
+  NBX_CUDA(cudaGetLastError());
+  s->built = true;
+  return NBX_OK;
+}
+
+template <typename T, int D>
+static int check_overflow(nbx_engine* e) {
+  auto* s = st<T>(e);
+  Root<T> h;
+  NBX_CUDA(cudaMemcpyAsync(&h, s->root, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
+  NBX_CUDA(cudaStreamSynchronize(e->stream));
+  e->d2h += sizeof(h);
+  if (h.overflow)
+    return fail(NBX_ERR_CAPACITY,
+                "octree: bodies not separated within the supported depth (coincident bodies?) or more cells than the "
+                "reference's capacity max(2^D*n,1000) (src/system.h:29) allows");
+  return NBX_OK;
+}
+
+template <typename T, int D>
+static int force_impl(nbx_engine* e) {
+  auto* s = st<T>(e);
+  if (!s->built) return fail(NBX_ERR_STATE, "octree compute_force before build");
+  const uint32_t nt = e->te - e->tb;
+  PhaseTimer pt(e, PH_TRAVERSE);
+  if (nt) {
+    octree_force_kernel<T, D><<<(nt + 127) / 128, 128, 0, e->stream>>>(s->mono, s->meta, s->root, s->cnt, e->n, e->tb, e->te,
+                                                                      T(e->cfg.theta), T(e->cfg.G), s->a_sorted);
+    e->launches++;
+  }
+  if (e->cfg.world_size > 1) NBX_TRY(comm_allgather(e, s->a_sorted));
+  unsort_kernel<T><<<(e->n + 255) / 256, 256, 0, e->stream>>>(s->perm, s->a_sorted, e->n, static_cast<vec4_t<T>*>(e->a));
+  e->launches++;
+  NBX_CUDA(cudaGetLastError());
+  return NBX_OK;
+}
+
+template <typename T, int D>
+static int get_root_impl(nbx_engine* e, void* side, void* root_x, uint64_t* nodes_used) {
+  auto* s = st<T>(e);
+  if (!s->built) return fail(NBX_ERR_STATE, "no octree build has run yet");
+  NBX_TRY((check_overflow<T, D>(e)));
+  Root<T> h;
+  NBX_CUDA(cudaMemcpy(&h, s->root, sizeof(h), cudaMemcpyDeviceToHost));
+  if (side) *static_cast<T*>(side) = h.side;
+  if (root_x)
+    for (int k = 0; k < D; ++k) static_cast<T*>(root_x)[k] = h.x;
+  if (nodes_used) *nodes_used = 1 + (uint64_t(1) << D) * h.cells;  // what next_free_child_group reads (octree.h:152)
+  return NBX_OK;
+}
+
+template <typename T, int D>
+static int get_canonical_impl(nbx_engine* e, uint64_t* count, uint32_t* depth, uint64_t* path, uint32_t* kind, void* monopole) {
+  auto* s = st<T>(e);
+  if (!s->built) return fail(NBX_ERR_STATE, "no octree build has run yet");
+  NBX_TRY((check_overflow<T, D>(e)));
+  Root<T> h;
+  NBX_CUDA(cudaMemcpy(&h, s->root, sizeof(h), cudaMemcpyDeviceToHost));
+  const uint32_t nrec = e->n + h.cells;
+  if (count) *count = nrec;
+  if (!depth && !path && !kind && !monopole) return NBX_OK;
+  if (!depth || !path || !kind || !monopole) return fail(NBX_ERR_INVALID, "octree_get_canonical: pass all arrays or none");
+  uint32_t *dd = nullptr, *dk = nullptr;
+  uint64_t* dp = nullptr;
+  T* dm        = nullptr;
+  NBX_CUDA(cudaMalloc(&dd, sizeof(uint32_t) * nrec));
+  NBX_CUDA(cudaMalloc(&dk, sizeof(uint32_t) * nrec));
+  NBX_CUDA(cudaMalloc(&dp, sizeof(uint64_t) * nrec));
+  NBX_CUDA(cudaMalloc(&dm, sizeof(T) * size_t(nrec) * (D + 1)));
+  export_canonical_kernel<T, D><<<(nrec + 255) / 256, 256, 0, e->stream>>>(s->mono, s->meta, s->rec_body, s->skeys, nrec, dd, dp, dk, dm);
+  e->launches++;
+  cudaError_t err = cudaMemcpyAsync(depth, dd, sizeof(uint32_t) * nrec, cudaMemcpyDeviceToHost, e->stream);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(kind, dk, sizeof(uint32_t) * nrec, cudaMemcpyDeviceToHost, e->stream);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(path, dp, sizeof(uint64_t) * nrec, cudaMemcpyDeviceToHost, e->stream);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(monopole, dm, sizeof(T) * size_t(nrec) * (D + 1), cudaMemcpyDeviceToHost, e->stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+  e->d2h += size_t(nrec) * (16 + sizeof(T) * (D + 1));
+  cudaFree(dd); cudaFree(dk); cudaFree(dp); cudaFree(dm);
+  if (err != cudaSuccess) return fail(NBX_ERR_CUDA, cudaGetErrorString(err));
+  return NBX_OK;
+}
+
+#define OCT_DISPATCH(e, fn, ...)                                                          \
+  ((e)->prec == 4 ? ((e)->dim == 2 ? fn<float, 2>(__VA_ARGS__) : fn<float, 3>(__VA_ARGS__)) \
+                  : ((e)->dim == 2 ? fn<double, 2>(__VA_ARGS__) : fn<double, 3>(__VA_ARGS__)))
+
+int octree_create(nbx_engine* e) { return OCT_DISPATCH(e, create_impl, e); }
+void octree_destroy(nbx_engine* e) {
+  if (!e->octree) return;
+  OCT_DISPATCH(e, destroy_impl, e);
+}
+int octree_build(nbx_engine* e) { return OCT_DISPATCH(e, build_impl, e); }
+int octree_compute_force(nbx_engine* e) { return OCT_DISPATCH(e, force_impl, e); }
+int octree_check(nbx_engine* e) { return OCT_DISPATCH(e, check_overflow, e); }
+int octree_get_root(nbx_engine* e, void* side, void* root_x, uint64_t* nodes_used) {
+  return OCT_DISPATCH(e, get_root_impl, e, side, root_x, nodes_used);
+}
+int octree_get_canonical(nbx_engine* e, uint64_t* count, uint32_t* depth, uint64_t* path, uint32_t* kind, void* monopole) {
+  return OCT_DISPATCH(e, get_canonical_impl, e, count, depth, path, kind, monopole);
+}
+
+}  // namespace nbx

@@ -84,8 +84,9 @@ def test_pipeline_vs_oracle(oracle, tag, dim, n):
     check_pipeline(oracle, oracle.galaxy(n, DT[tag], dim))
 
 
-def test_pipeline_vs_oracle_65536(oracle_fast):
-    check_pipeline(oracle_fast, oracle_fast.galaxy(65536, np.float32, 3), thetas=(THETA,))
+def test_pipeline_vs_oracle_65536(oracle):
+    # the pinned (-O2, no contraction) oracle: the -Ofast build changes float keys
+    check_pipeline(oracle, oracle.galaxy(65536, np.float32, 3), thetas=(THETA,))
 
 
 @pytest.mark.parametrize("tag,dim", CASES, ids=IDS)
@@ -140,7 +141,6 @@ def test_sort_properties_10M():
         xs = e.download(("x",))["x"]
     assert np.array_equal(np.bincount(perm, minlength=n), np.ones(n, np.int64))
     ks = keys[perm]
-    d = np.diff(ks.astype(np.int64) >> 1) if False else None  # (uint64 diff done below without overflow)
     assert (ks[1:] >= ks[:-1]).all()
     eq = ks[1:] == ks[:-1]
     assert (perm[1:][eq] > perm[:-1][eq]).all()
