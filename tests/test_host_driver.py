@@ -94,8 +94,15 @@ def test_final_state_print_matches_reference_binary(algo, dim, prec):
     and 1: src/system.h:92-94) must be textually identical. -s 12 => 10 warm-up + 2 timed steps."""
     args = ["-n", "64", "-s", "12", "--workload", "galaxy", "--algorithm", algo, "--precision", prec, "--theta", "0.5",
             "--print-state"]
+    ref_exe = os.path.join(O.REF_DIR, f"nbody_d{dim}")
+    if algo == "bvh" and dim == 2 and prec == "float":
+        # 2-D float Hilbert keys hit the float->u32 overflow that is UB in the reference (SURVEY §9 Q6): only the
+        # AVX-512 -march=native build saturates like CUDA does; the generic build wraps and sorts 2 bodies elsewhere.
+        ref_exe = os.path.join(O.REF_DIR, "nbody_d2_native")
+        if not (O.avx512_host() and os.access(ref_exe, os.X_OK)):
+            pytest.skip("needs the AVX-512 native reference build")
     mine = run(dim, args).stdout
-    ref = subprocess.run([os.path.join(O.REF_DIR, f"nbody_d{dim}")] + args, capture_output=True, text=True).stdout
+    ref = subprocess.run([ref_exe] + args, capture_output=True, text=True).stdout
 
     def strip(out):
         return [ln for ln in out.splitlines() if not ln.startswith("Total time")]
