@@ -13,6 +13,7 @@
 // of each target block, which also applies the leapfrog update (fused epilogue, double-buffered positions).
 #include <cfloat>
 #include <cstdio>
+#include <cstdlib>
 
 #include "nbx_internal.cuh"
 
@@ -49,6 +50,24 @@ __device__ __forceinline__ double inv_dist3(double d2) {
   inv       = fma(inv, e2, inv);
   return inv;
 }
+
+// One-MUFU variant used for a fraction of the float pairs (see all_pairs_kernel, NB): with q = rsqrt(d2)^3 = 1/d2^1.5,
+//   m/(d2^1.5 + eps) = m*q/(1 + eps*q) = m*q*(1 - u + u^2 - ...),  u = eps*q.
+// The first-order form m*q*(1-u) is exact to u^2 <= 2^-24 while q <= Q_CAP = 2^-12/eps = 2048 (pairs farther apart than
+// 0.079); `qmax` records the largest q seen so that the caller can redo the (rare) tiles that contain a closer pair — or
+// the self pair, whose q is +inf — with the exact two-MUFU formula. XU work per pair drops from 2 to 1 MUFU at the price
+// of 3 more FMA-pipe instructions and one FMNMX.
+constexpr float AP_Q_CAP = 2048.0f;
+__device__ __forceinline__ float scaled_inv_dist3_rsq(float d2, float m, float& qmax) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d2));  // MUFU.RSQ
+  const float q = (r * r) * r;
+  qmax          = fmaxf(qmax, q);
+  const float mq = m * q;
+  const float u  = q * FLT_EPSILON;
+  return fmaf(-u, mq, mq);
+}
+__device__ __forceinline__ double scaled_inv_dist3_rsq(double d2, double m, double&) { return m * inv_dist3(d2); }
 
 // round-to-nearest ops that the compiler may not contract: the leapfrog restates system.h:56-58 operation by
 // operation so that, given the same `a`, it is bit-identical to the pinned (-ffp-contract=off) reference.
@@ -154,8 +173,9 @@ struct AllPairsArgs {
   LeapArgs<T> leap;      // leap.a is also the destination of the acceleration
 };
 
-template <typename T, int D, int TI, int BLOCK, int TILE, int STAGES, int MINB>
+template <typename T, int D, int TI, int BLOCK, int TILE, int STAGES, int MINB, int NB, int UNROLL = 4>
 __global__ void __launch_bounds__(BLOCK, MINB) all_pairs_kernel(AllPairsArgs<T> p) {
+  static_assert(NB >= 0 && NB < TI || NB == 0, "NB targets of each thread use the one-MUFU path");
   using V4 = vec4_t<T>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   V4* tiles      = reinterpret_cast<V4*>(smem_raw);
@@ -197,7 +217,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) all_pairs_kernel(AllPairsArgs<T> 
     const int stage = k % STAGES;
     mbar_wait(&bars[stage], (k / STAGES) & 1);
     const V4* tile = tiles + size_t(stage) * TILE;
-#pragma unroll 4
+    // snapshot of the accumulators of the NB one-MUFU targets, restored if this tile has to be redone exactly
+    T sx[NB ? NB : 1], sy[NB ? NB : 1], sz[NB ? NB : 1];
+    T qmax = T(0);
+#pragma unroll
+    for (int t = 0; t < NB; ++t) { sx[t] = ax[TI - NB + t]; sy[t] = ay[TI - NB + t]; sz[t] = az[TI - NB + t]; }
+#pragma unroll UNROLL
     for (int j = 0; j < TILE; ++j) {
       const V4 b = tile[j];  // broadcast LDS.128 (2x for double)
 #pragma unroll
@@ -210,10 +235,33 @@ __global__ void __launch_bounds__(BLOCK, MINB) all_pairs_kernel(AllPairsArgs<T> 
           dz = b.z - zi[t];
           d2 = fma(dz, dz, d2);
         }
-        T s   = b.w * inv_dist3(d2);
+        T s   = t < TI - NB ? b.w * inv_dist3(d2) : scaled_inv_dist3_rsq(d2, b.w, qmax);
         ax[t] = fma(dx, s, ax[t]);
         ay[t] = fma(dy, s, ay[t]);
         if (D == 3) az[t] = fma(dz, s, az[t]);
+      }
+    }
+    if (NB > 0 && !(qmax <= T(AP_Q_CAP))) {  // a close (or the self) pair in this tile: redo it with the exact formula
+#pragma unroll
+      for (int t = 0; t < NB; ++t) { ax[TI - NB + t] = sx[t]; ay[TI - NB + t] = sy[t]; az[TI - NB + t] = sz[t]; }
+#pragma unroll 2
+      for (int j = 0; j < TILE; ++j) {
+        const V4 b = tile[j];
+#pragma unroll
+        for (int t = TI - NB; t < TI; ++t) {
+          T dx = b.x - xi[t];
+          T dy = b.y - yi[t];
+          T d2 = fma(dy, dy, dx * dx);
+          T dz = T(0);
+          if (D == 3) {
+            dz = b.z - zi[t];
+            d2 = fma(dz, dz, d2);
+          }
+          T s   = b.w * inv_dist3(d2);
+          ax[t] = fma(dx, s, ax[t]);
+          ay[t] = fma(dy, s, ay[t]);
+          if (D == 3) az[t] = fma(dz, s, az[t]);
+        }
       }
     }
     __syncthreads();  // every warp is done with this stage: safe to overwrite it
@@ -463,9 +511,9 @@ static LeapArgs<T> make_leap(nbx_engine* e, bool to_next) {
 constexpr int AP_TILE   = 512;  // bodies per shared-memory tile (also the zero-mass padding appended to xm)
 constexpr int AP_STAGES = 4;
 
-template <typename T, int D, int TI, int BLOCK, int MINB>
+template <typename T, int D, int TI, int BLOCK, int MINB, int NB = 0, int UNROLL = 4>
 static int launch_all_pairs_cfg(nbx_engine* e, bool fuse, uint32_t nsplit, uint32_t tiles_per_split) {
-  auto kern = all_pairs_kernel<T, D, TI, BLOCK, AP_TILE, AP_STAGES, MINB>;
+  auto kern = all_pairs_kernel<T, D, TI, BLOCK, AP_TILE, AP_STAGES, MINB, NB, UNROLL>;
   const size_t smem = size_t(AP_STAGES) * AP_TILE * sizeof(vec4_t<T>) + AP_STAGES * sizeof(uint64_t);
   static bool attr_done = false;  // per template instantiation
   if (!attr_done) {
@@ -517,7 +565,10 @@ static int launch_all_pairs(nbx_engine* e, bool fuse) {
   const uint32_t tiles_total = (e->n + AP_TILE - 1) / AP_TILE;
   // pick the target register blocking so that small problems still fill the chip
   constexpr int TI_MAX = sizeof(T) == 4 ? 4 : 2;
+  static const int var = [] { const char* v = getenv("NBX_AP_VAR"); return v ? atoi(v) : 0; }();
   int ti               = TI_MAX;
+  if (sizeof(T) == 4 && (var == 3 || var == 4)) ti = 2;
+  if (sizeof(T) == 4 && var == 5) ti = 8;
   const uint32_t want  = uint32_t(e->sm_count) * 4;
   while (ti > 1 && ((nt + 256 * ti - 1) / (256 * ti)) * tiles_total < want * 4) ti >>= 1;
   const int block        = 256;
@@ -531,6 +582,16 @@ static int launch_all_pairs(nbx_engine* e, bool fuse) {
   uint32_t tps = (tiles_total + nsplit - 1) / nsplit;
   nsplit       = (tiles_total + tps - 1) / tps;
   if constexpr (sizeof(T) == 4) {
+    static const int mix = [] { const char* v = getenv("NBX_AP_MIX"); return v ? atoi(v) : 0; }();
+    if (var == 1 && ti == 4) return launch_all_pairs_cfg<T, D, 4, 256, 3, 0, 8>(e, fuse, nsplit, tps);
+    if (var == 2 && ti == 4) return launch_all_pairs_cfg<T, D, 4, 256, 4, 0, 4>(e, fuse, nsplit, tps);
+    if (var == 3 && ti == 2) return launch_all_pairs_cfg<T, D, 2, 256, 4, 0, 8>(e, fuse, nsplit, tps);
+    if (var == 4 && ti == 2) return launch_all_pairs_cfg<T, D, 2, 256, 6, 0, 4>(e, fuse, nsplit, tps);
+    if (var == 5 && ti == 8) return launch_all_pairs_cfg<T, D, 8, 256, 2, 0, 2>(e, fuse, nsplit, tps);
+    if (var == 6 && ti == 4) return launch_all_pairs_cfg<T, D, 4, 256, 3, 0, 2>(e, fuse, nsplit, tps);
+    if (var == 7 && ti == 4) return launch_all_pairs_cfg<T, D, 4, 256, 3, 2, 8>(e, fuse, nsplit, tps);
+    if (ti == 4 && mix == 1) return launch_all_pairs_cfg<T, D, 4, 256, 3, 1>(e, fuse, nsplit, tps);
+    if (ti == 4 && mix == 2) return launch_all_pairs_cfg<T, D, 4, 256, 3, 2>(e, fuse, nsplit, tps);
     if (ti == 4) return launch_all_pairs_cfg<T, D, 4, 256, 3>(e, fuse, nsplit, tps);
     if (ti == 2) return launch_all_pairs_cfg<T, D, 2, 256, 3>(e, fuse, nsplit, tps);
     return launch_all_pairs_cfg<T, D, 1, 256, 3>(e, fuse, nsplit, tps);

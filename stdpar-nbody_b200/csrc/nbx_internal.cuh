@@ -136,8 +136,10 @@ int sorter_create(nbx_engine* e, uint32_t n);
 void sorter_destroy(nbx_engine* e);
 // sorts keys_in (device, n) -> perm_out (device, n): perm_out[i] = index of the i-th smallest key (ties by index).
 // keys_sorted_out (optional) receives the sorted keys. `key_bits` = number of significant low bits.
+// `vals_in` (optional, must not alias the sorter's internal buffers or perm_out) replaces the implicit iota payload,
+// so that a second, more significant key can be sorted on top of an earlier permutation (LSD over two words).
 int sort_pairs(nbx_engine* e, const uint64_t* keys_in, uint32_t n, int key_bits, uint32_t* perm_out,
-               uint64_t* keys_sorted_out);
+               uint64_t* keys_sorted_out, const uint32_t* vals_in = nullptr);
 // nbx_bvh.cu
 int bvh_create(nbx_engine* e);
 void bvh_destroy(nbx_engine* e);

@@ -55,8 +55,13 @@ struct OctreeState {
   Root<T>* root      = nullptr;
   T* partial         = nullptr;  // [blocks][2]
   uint32_t nblocks   = 0;
-  uint64_t* keys     = nullptr;  // path keys, entry order
+  uint64_t* keys     = nullptr;  // path keys (levels 1..MAXL), entry order
   uint64_t* skeys    = nullptr;  // sorted
+  uint64_t* keys_lo  = nullptr;  // deep mode: levels MAXL+1..2*MAXL, entry order / scratch
+  uint64_t* skeys_lo = nullptr;  // deep mode: sorted low words (all zero in shallow mode)
+  uint64_t* keys_tmp = nullptr;  // deep mode scratch
+  uint32_t* perm_tmp = nullptr;  // deep mode scratch
+  bool deep          = false;    // the last build needed more than MAXL levels
   uint32_t* perm     = nullptr;  // sorted slot -> body id
   uint32_t* delta    = nullptr;  // [n] common-prefix levels of sorted neighbours s, s+1 (MAXL+1.. see kernel)
   uint32_t* cnt      = nullptr;  // [n+1] cells starting at sorted body s -> exclusive scan in place (cell_base)
@@ -112,7 +117,8 @@ __global__ void bounds_final_kernel(const T* partial, uint32_t nblocks, Root<T>*
 // ---- K7 path keys -------------------------------------------------------------------------------------------------
 template <typename T, int D>
 __global__ void __launch_bounds__(256) path_keys_kernel(const vec4_t<T>* __restrict__ xm, uint32_t n,
-                                                        const Root<T>* __restrict__ root, uint64_t* __restrict__ keys) {
+                                                        const Root<T>* __restrict__ root, uint64_t* __restrict__ keys,
+                                                        uint64_t* __restrict__ keys_lo /* NULL: first MAXL levels only */) {
   uint32_t i = blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   vec4_t<T> b = xm[i];
@@ -134,6 +140,28 @@ __global__ void __launch_bounds__(256) path_keys_kernel(const vec4_t<T>* __restr
     key  = (key << D) | cp;
   }
   keys[i] = key;
+  if (keys_lo == nullptr) return;
+  key = 0;  // the same descent, MAXL more levels
+#pragma unroll 1
+  for (int level = 0; level < KeyTraits<D>::MAXL; ++level) {
+    const T half = div_rn(side, T(4));
+    uint32_t cp  = 0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const bool gt = pos[k] > divide[k];
+      cp |= uint32_t(gt) << k;
+      divide[k] = add_rn(divide[k], gt ? half : -half);
+    }
+    side = div_rn(side, T(2));
+    key  = (key << D) | cp;
+  }
+  keys_lo[i] = key;
+}
+
+__global__ void __launch_bounds__(256) gather_u64_kernel(const uint64_t* __restrict__ src, const uint32_t* __restrict__ idx,
+                                                         uint32_t n, uint64_t* __restrict__ dst) {
+  uint32_t i = blockIdx.x * 256 + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
 }
 
 // ---- cells --------------------------------------------------------------------------------------------------------
@@ -145,17 +173,39 @@ __device__ __forceinline__ uint32_t common_levels(uint64_t a, uint64_t b) {
   return uint32_t(lead / D);
 }
 
+// two-word keys: levels 1..MAXL in `hi`, MAXL+1..2*MAXL in `lo` (lo == NULL: shallow mode)
+template <int D>
+__device__ __forceinline__ uint32_t common_levels2(const uint64_t* hi, const uint64_t* lo, uint32_t a, uint32_t b) {
+  uint32_t c = common_levels<D>(hi[a], hi[b]);
+  if (c == KeyTraits<D>::MAXL && lo) c += common_levels<D>(lo[a], lo[b]);
+  return c;
+}
+// the first `depth` digits of sorted body i, as (word, value): equal prefixes <=> equal pairs
+template <int D>
+__device__ __forceinline__ bool same_prefix(const uint64_t* hi, const uint64_t* lo, uint32_t a, uint32_t b, uint32_t depth) {
+  constexpr int MAXL = KeyTraits<D>::MAXL;
+  if (depth == 0) return true;
+  if (depth <= MAXL) {
+    const int shift = D * (MAXL - int(depth));
+    return shift >= 64 ? true : (hi[a] >> shift) == (hi[b] >> shift);
+  }
+  if (hi[a] != hi[b]) return false;
+  const int shift = D * (2 * MAXL - int(depth));
+  return shift >= 64 ? true : (lo[a] >> shift) == (lo[b] >> shift);
+}
+
 // delta[s] = levels shared by sorted bodies s and s+1 (s < n-1); cnt[s] = number of cells whose first body is s
 template <int D>
-__global__ void __launch_bounds__(256) delta_kernel(const uint64_t* __restrict__ skeys, uint32_t n, uint32_t* delta,
-                                                    uint32_t* cnt, uint32_t* overflow) {
+__global__ void __launch_bounds__(256) delta_kernel(const uint64_t* __restrict__ skeys, const uint64_t* __restrict__ skeys_lo,
+                                                    uint32_t n, uint32_t* delta, uint32_t* cnt, uint32_t* overflow) {
   uint32_t s = blockIdx.x * 256 + threadIdx.x;
   if (s > n) return;
   if (s == n) { cnt[n] = 0; return; }
   // shared levels with the next / previous body; "-1" is encoded by computing with +1 offsets
-  uint32_t dn = s + 1 < n ? common_levels<D>(skeys[s], skeys[s + 1]) + 1 : 0;  // delta_s + 1   (0 = none)
-  uint32_t dp = s > 0 ? common_levels<D>(skeys[s - 1], skeys[s]) + 1 : 0;      // delta_{s-1} + 1
-  if (dn == KeyTraits<D>::MAXL + 1) atomicExch(overflow, 1u);                  // coincident within MAXL levels
+  uint32_t dn = s + 1 < n ? common_levels2<D>(skeys, skeys_lo, s, s + 1) + 1 : 0;  // delta_s + 1   (0 = none)
+  uint32_t dp = s > 0 ? common_levels2<D>(skeys, skeys_lo, s - 1, s) + 1 : 0;      // delta_{s-1} + 1
+  const uint32_t maxl = skeys_lo ? 2 * KeyTraits<D>::MAXL : KeyTraits<D>::MAXL;
+  if (dn == maxl + 1) atomicExch(overflow, 1u);  // not separated within the available levels
   delta[s] = dn;
   cnt[s]   = dn > dp ? dn - dp : 0;
 }
@@ -247,14 +297,14 @@ __global__ void __launch_bounds__(1024) scan_apply_kernel(uint32_t* data, uint32
 // Record index of cell (s, depth d) = s + cell_id, cell_id = cell_base[s] + (d - first depth); of leaf s = s + cell_base[s+1].
 // `next` of a cell = record index right after its last body e: (e + 1) + cell_base[e + 1].
 template <typename T, int D>
-__global__ void __launch_bounds__(256) emit_records_kernel(const uint64_t* __restrict__ skeys, const uint32_t* __restrict__ perm,
+__global__ void __launch_bounds__(256) emit_records_kernel(const uint64_t* __restrict__ skeys, const uint64_t* __restrict__ skeys_lo,
+                                                           const uint32_t* __restrict__ perm,
                                                            const vec4_t<T>* __restrict__ xm, uint32_t n,
                                                            const uint32_t* __restrict__ delta, const uint32_t* __restrict__ cell_base,
                                                            uint32_t cap, vec4_t<T>* mono, uint2* meta, uint32_t* rec_body,
                                                            uint32_t* cell_pos, Root<T>* root) {
   uint32_t s = blockIdx.x * 256 + threadIdx.x;
   if (s >= n) return;
-  constexpr int MAXL = KeyTraits<D>::MAXL;
   const uint32_t dn = delta[s];                      // delta_s + 1
   const uint32_t dp = s > 0 ? delta[s - 1] : 0;      // delta_{s-1} + 1
   const uint32_t cb = cell_base[s], cb_next = cell_base[s + 1];
@@ -271,17 +321,13 @@ __global__ void __launch_bounds__(256) emit_records_kernel(const uint64_t* __res
     rec_body[lpos] = s;
   }
   if (dn <= dp) return;
-  const uint64_t key = skeys[s];
   for (uint32_t q = 0; q < dn - dp; ++q) {
     const uint32_t depth = dp + q;  // cells at depths delta_{s-1}+1 .. delta_s  (dp = delta_{s-1}+1)
     // last body e sharing `depth` digits with s: binary search on the sorted keys
-    const int shift   = D * (MAXL - int(depth));
-    const uint64_t pf = depth == 0 ? 0 : (shift >= 64 ? 0 : key >> shift);
     uint32_t lo = s, hi = n - 1;  // invariant: lo shares the prefix
     while (lo < hi) {
       uint32_t mid = lo + (hi - lo + 1) / 2;
-      uint64_t pm  = depth == 0 ? 0 : (shift >= 64 ? 0 : skeys[mid] >> shift);
-      if (pm == pf) lo = mid;
+      if (same_prefix<D>(skeys, skeys_lo, s, mid, depth)) lo = mid;
       else hi = mid - 1;
     }
     const uint32_t e   = lo;
@@ -402,7 +448,8 @@ __global__ void export_canonical_kernel(const vec4_t<T>* mono, const uint2* meta
   depth[p]         = d;
   kind[p]          = (me.y & LEAF_FLAG) ? 1u : 0u;
   const int shift  = D * (KeyTraits<D>::MAXL - int(d));
-  path[p]          = d == 0 ? 0 : (shift >= 64 ? 0 : skeys[rec_body[p]] >> shift);
+  // the u64 path code only holds MAXL levels: deeper nodes (two-word keys) export ~0
+  path[p]          = d == 0 ? 0 : (shift < 0 ? ~0ull : (shift >= 64 ? 0 : skeys[rec_body[p]] >> shift));
   vec4_t<T> m      = mono[p];
   T* om            = out_m + size_t(p) * (D + 1);
   om[0] = m.x; om[1] = m.y;
@@ -427,6 +474,10 @@ static int create_impl(nbx_engine* e) {
   NBX_CUDA(cudaMalloc(&s->partial, sizeof(T) * 2 * s->nblocks));
   NBX_CUDA(cudaMalloc(&s->keys, sizeof(uint64_t) * n));
   NBX_CUDA(cudaMalloc(&s->skeys, sizeof(uint64_t) * n));
+  NBX_CUDA(cudaMalloc(&s->keys_lo, sizeof(uint64_t) * n));
+  NBX_CUDA(cudaMalloc(&s->skeys_lo, sizeof(uint64_t) * n));
+  NBX_CUDA(cudaMalloc(&s->keys_tmp, sizeof(uint64_t) * n));
+  NBX_CUDA(cudaMalloc(&s->perm_tmp, sizeof(uint32_t) * n));
   NBX_CUDA(cudaMalloc(&s->perm, sizeof(uint32_t) * n));
   NBX_CUDA(cudaMalloc(&s->delta, sizeof(uint32_t) * n));
   NBX_CUDA(cudaMalloc(&s->cnt, sizeof(uint32_t) * (n + 1)));
@@ -445,7 +496,7 @@ template <typename T, int D>
 static void destroy_impl(nbx_engine* e) {
   auto* s = st<T>(e);
   if (!s) return;
-  void* bufs[] = {s->root, s->partial, s->keys, s->skeys, s->perm, s->delta, s->cnt, s->blocksum,
+  void* bufs[] = {s->root, s->partial, s->keys, s->skeys, s->keys_lo, s->skeys_lo, s->keys_tmp, s->perm_tmp, s->perm, s->delta, s->cnt, s->blocksum,
                   s->mono, s->meta, s->rec_body, s->cell_pos, s->a_sorted};
   for (void* b : bufs)
     if (b) cudaFree(b);
@@ -467,24 +518,42 @@ static int build_impl(nbx_engine* e) {
   }
   {
     PhaseTimer pt(e, PH_SORT);
-    path_keys_kernel<T, D><<<gb, 256, 0, e->stream>>>(xm, n, s->root, s->keys);
+    path_keys_kernel<T, D><<<gb, 256, 0, e->stream>>>(xm, n, s->root, s->keys, nullptr);
     e->launches++;
     NBX_TRY(sort_pairs(e, s->keys, n, KeyTraits<D>::BITS, s->perm, s->skeys));
+    delta_kernel<D><<<(n + 1 + 255) / 256, 256, 0, e->stream>>>(s->skeys, nullptr, n, s->delta, s->cnt, &s->root->overflow);
+    e->launches++;
+    // MAXL levels (21 in 3-D, 32 in 2-D) separate all bodies of the usual workloads; if two bodies still share a cell the
+    // build is redone with two-word keys (2*MAXL levels): LSD sort by the low word, then by the high word.
+    uint32_t ovf = 0;
+    NBX_CUDA(cudaMemcpyAsync(&ovf, &s->root->overflow, sizeof(ovf), cudaMemcpyDeviceToHost, e->stream));
+    NBX_CUDA(cudaStreamSynchronize(e->stream));
+    e->d2h += sizeof(ovf);
+    s->deep = ovf != 0;
+    if (s->deep) {
+      NBX_CUDA(cudaMemsetAsync(&s->root->overflow, 0, sizeof(uint32_t), e->stream));
+      path_keys_kernel<T, D><<<gb, 256, 0, e->stream>>>(xm, n, s->root, s->keys, s->keys_lo);
+      NBX_TRY(sort_pairs(e, s->keys_lo, n, KeyTraits<D>::BITS, s->perm_tmp, nullptr));
+      gather_u64_kernel<<<gb, 256, 0, e->stream>>>(s->keys, s->perm_tmp, n, s->keys_tmp);
+      NBX_TRY(sort_pairs(e, s->keys_tmp, n, KeyTraits<D>::BITS, s->perm, s->skeys, s->perm_tmp));
+      gather_u64_kernel<<<gb, 256, 0, e->stream>>>(s->keys_lo, s->perm, n, s->skeys_lo);
+      delta_kernel<D><<<(n + 1 + 255) / 256, 256, 0, e->stream>>>(s->skeys, s->skeys_lo, n, s->delta, s->cnt, &s->root->overflow);
+      e->launches += 4;
+    }
   }
   {
     PhaseTimer pt(e, PH_BUILD);
-    delta_kernel<D><<<(n + 1 + 255) / 256, 256, 0, e->stream>>>(s->skeys, n, s->delta, s->cnt, &s->root->overflow);
     const uint32_t count = n + 1, nb = (count + SC_TILE - 1) / SC_TILE;
     scan_reduce_kernel<<<nb, 1024, 0, e->stream>>>(s->cnt, count, s->blocksum);
     scan_blocksums_kernel<<<1, 1024, 0, e->stream>>>(s->blocksum, nb, nullptr);
     scan_apply_kernel<<<nb, 1024, 0, e->stream>>>(s->cnt, count, s->blocksum);
-    emit_records_kernel<T, D><<<gb, 256, 0, e->stream>>>(s->skeys, s->perm, xm, n, s->delta, s->cnt, s->cap, s->mono, s->meta,
-                                                        s->rec_body, s->cell_pos, s->root);
-    e->launches += 5;
+    emit_records_kernel<T, D><<<gb, 256, 0, e->stream>>>(s->skeys, s->deep ? s->skeys_lo : nullptr, s->perm, xm, n, s->delta, s->cnt,
+                                                        s->cap, s->mono, s->meta, s->rec_body, s->cell_pos, s->root);
+    e->launches += 4;
   }
   {
     PhaseTimer pt(e, PH_MONO);
-    for (int depth = KeyTraits<D>::MAXL - 1; depth >= 0; --depth) {
+    for (int depth = (s->deep ? 2 : 1) * KeyTraits<D>::MAXL - 1; depth >= 0; --depth) {
       monopole_level_kernel<T, D><<<gb, 256, 0, e->stream>>>(s->cell_pos, s->root, uint32_t(depth), s->cap, s->mono, s->meta);
       e->launches++;
     }

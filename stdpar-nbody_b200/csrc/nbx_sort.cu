@@ -190,7 +190,7 @@ void sorter_destroy(nbx_engine* e) {
 }
 
 int sort_pairs(nbx_engine* e, const uint64_t* keys_in, uint32_t n, int key_bits, uint32_t* perm_out,
-               uint64_t* keys_sorted_out) {
+               uint64_t* keys_sorted_out, const uint32_t* vals_in) {
   NBX_TRY(sorter_create(e, n));
   Sorter* s = static_cast<Sorter*>(e->sorter);
   if (n > s->capacity) return fail(NBX_ERR_INVALID, "sort_pairs: n exceeds sorter capacity");
@@ -199,7 +199,7 @@ int sort_pairs(nbx_engine* e, const uint64_t* keys_in, uint32_t n, int key_bits,
   if (passes < 1) passes = 1;
   if (passes > 8) passes = 8;
   const uint64_t* kin = keys_in;
-  const uint32_t* vin = nullptr;  // iota
+  const uint32_t* vin = vals_in;  // nullptr => iota
   for (int p = 0; p < passes; ++p) {
     const bool last = p == passes - 1;
     uint64_t* kout  = last && keys_sorted_out ? keys_sorted_out : s->keys[p & 1];

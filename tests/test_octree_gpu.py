@@ -103,6 +103,31 @@ def test_theta0_equals_all_pairs(oracle):
     assert rel_err(a, ap).max() < 1e-10
 
 
+@pytest.mark.parametrize("tag,dim,gap", [("f64", 3, 1e-7), ("f64", 2, 1e-9), ("f32", 3, 2e-5)])
+def test_deep_tree_two_word_keys(oracle, tag, dim, gap):
+    """Two bodies closer than the 21-level (3-D) / 32-level (2-D) cell size: the build falls back to two-word keys and
+    still reproduces the reference's (deeper) tree: same depths/kinds/monopoles in DFS order, same forces."""
+    dt = DT[tag]
+    s = oracle.galaxy(600, dt, dim)
+    s["x"][41] = s["x"][40]
+    s["x"][41, 0] += dt(gap)
+    t = oracle.octree_build(s["m"], s["x"])
+    depth, path, kind, mo = oracle.octree_canonical(t, dim)
+    assert depth.max() > (21 if dim == 3 else 32)
+    with engine(s) as e:
+        e.octree_build()
+        side, root, used = e.octree_root()
+        assert used == t["used"]
+        gd, gp, gk, gm = e.octree_canonical()
+        assert same(gd, depth) and same(gk, kind) and same(gm, mo)
+        e.octree_compute_force()
+        a = e.download(("a",))["a"]
+    ref, _ = oracle.octree_force(s["x"], t, s["G"], THETA)
+    tr, tm = TOL[np.dtype(dt)]
+    err = rel_err(a, ref)
+    assert rms(err) <= tr and err.max() <= 10 * tm, (rms(err), err.max())
+
+
 def test_coincident_bodies_are_reported(oracle):
     """The reference splits forever on coincident bodies (no capacity check, octree.h:146-169); nbx reports it."""
     s = oracle.galaxy(64, np.float32, 3)
