@@ -280,6 +280,11 @@ def main_nbx(args):
     ph = eng.phase_ms()
     eng.set_phase_timing(False)
 
+    tree_stats = None
+    ts_, te_ = nbx.shard_bounds(n, rank, world)
+    if args.algorithm in ("octree", "bvh"):
+        tree_stats = eng.traversal_stats()  # counting re-run of the last tree's walk (outside every timed region)
+
     # ---- end to end through the C ABI with host buffers --------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -335,9 +340,22 @@ def main_nbx(args):
                 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
             except OSError:
                 pass
-            roofline = {"bound": "hbm", "achieved": None, "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s",
-                        "frac": None, "traffic": None, "phase_ms": ph,
-                        "note": "peak = MEASURED_PEAKS.json hbm_gbs" if peaks else "peak = fallback 6.65 TB/s"}
+            peak = peaks.get("hbm_gbs", 6650.0)
+            # dominant kernel = the traversal; algorithmic bytes = (body, node) tests x node record size
+            # (octree monopole + link record 24/40 B, bvh monopole + width 20/40 B)
+            isz = np.dtype(dt).itemsize
+            rec = (4 * isz + 8) if args.algorithm == "octree" else (4 * isz + isz)
+            st = tree_stats
+            gbs = st["node_visits"] * rec / (ph["traverse"] * 1e-3) / 1e9 if ph.get("traverse") else None
+            roofline = {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s",
+                        "frac": gbs / peak if gbs else None, "traffic": None, "kernel": f"{args.algorithm}_force kernel",
+                        "kernel_ms": ph.get("traverse"), "node_bytes": rec,
+                        "visits_per_body": st["node_visits"] / max(1, te_ - ts_),
+                        "interactions_per_body": st["interactions"] / max(1, te_ - ts_),
+                        "lane_utilisation": st["node_visits"] / max(1, 32 * st["warp_steps"]),
+                        "note": ("achieved = requested node bytes (visits x record) / traversal time: an optimistic bound, "
+                                 "the records are served mostly from L1/L2; peak = "
+                                 + ("MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s"))}
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32" if dt == np.float32 else "f64",

@@ -132,11 +132,16 @@ int nbx_comm_init_rank(nbx_engine* e, const void* id128);
 /* FMA-pipe peak microbenchmark on the engine's device: precision NBX_F32 -> FFMA, NBX_F64 -> DFMA.
  * *tflops = 2 * fma/s / 1e12 measured with CUDA events. */
 int nbx_measure_fma_peak(int device, int precision, double* tflops);
+/* Tree engines: re-runs the traversal of the LAST built tree in counting mode (no state is modified) and returns, for
+ * this rank's targets, the number of (body, node) tests, of accepted interactions (body-level pairs count as one), and
+ * of warp-level steps (= records loaded per warp). Used for the HBM/L2 roofline of the walk: algorithmic bytes =
+ * node_visits x node record size. */
+int nbx_traversal_stats(nbx_engine* e, uint64_t* node_visits, uint64_t* interactions, uint64_t* warp_steps);
 /* counters of the engine since creation: kernels launched by this library, bytes copied H2D / D2H */
 int nbx_get_counters(nbx_engine* e, uint64_t* kernel_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
-/* per-phase device time (ms) of the last nbx_step* call's LAST step, in the reference's CSV column order:
- * all-pairs: force, accel; bvh: bbox, sort, multipoles, force approx, accel; octree: clear+bbox(bounds),
- * insert(build), multipoles, force approx, accel. Needs nbx_set_phase_timing(e,1). */
+/* per-phase device time (ms) of the last nbx_step* call's LAST step;
+ * slot order: 0 force (all-pairs), 1 accel, 2 bbox/bounds, 3 sort (+keys), 4 build (octree cells), 5 multipoles
+ * (bvh build_tree / octree monopoles), 6 traverse, 7 comm. Needs nbx_set_phase_timing(e,1). */
 int nbx_set_phase_timing(nbx_engine* e, int enable);
 int nbx_get_phase_ms(nbx_engine* e, float* ms, int capacity, int* count);
 

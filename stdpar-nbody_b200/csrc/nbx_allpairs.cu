@@ -16,40 +16,9 @@
 #include <cstdlib>
 
 #include "nbx_internal.cuh"
+#include "nbx_math.cuh"
 
 namespace nbx {
-
-// ---- math -----------------------------------------------------------------------------------------------------
-// 1 / (d2^1.5 + eps)   (vec.h:249-252 dist3; eps = numeric_limits<T>::epsilon()).  d2 == 0 gives 1/eps (finite), so a
-// self pair contributes m * 0 * (1/eps) = 0 exactly as `m*(pj-pi)/dist3` does in the reference, without a branch.
-__device__ __forceinline__ float inv_dist3(float d2) {
-  float sq, inv;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(d2));          // MUFU.SQRT
-  float den = fmaf(d2, sq, FLT_EPSILON);
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(den));         // MUFU.RCP
-  return inv;
-}
-__device__ __forceinline__ double inv_dist3(double d2) {
-  // rsqrt seed (MUFU.RSQ64H) refined on the FP64 pipe: one cubic step on y, then a Heron correction on sqrt.
-  double d2c = fmax(d2, 1e-300);
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d2c));
-  double t = d2c * y;
-  double e = fma(-t, y, 1.0);
-  double q = e * fma(0.375, e, 0.5);
-  y        = fma(y, q, y);
-  double sq = d2 * y;                       // d2 == 0 -> 0
-  double r  = fma(-sq, sq, d2);
-  sq        = fma(r, 0.5 * y, sq);
-  double den = fma(d2, sq, DBL_EPSILON);
-  double inv;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(inv) : "d"(den));        // MUFU.RCP64H
-  double e1 = fma(-den, inv, 1.0);
-  inv       = fma(inv, fma(e1, e1, e1), inv);
-  double e2 = fma(-den, inv, 1.0);
-  inv       = fma(inv, e2, inv);
-  return inv;
-}
 
 // One-MUFU variant used for a fraction of the float pairs (see all_pairs_kernel, NB): with q = rsqrt(d2)^3 = 1/d2^1.5,
 //   m/(d2^1.5 + eps) = m*q/(1 + eps*q) = m*q*(1 - u + u^2 - ...),  u = eps*q.

@@ -13,8 +13,10 @@
 // test `bw^2 < theta^2 * dist2` with the same exact arithmetic (identical interaction sets) and only the accumulated
 // force uses the fast MUFU path (tolerance-level difference).
 #include <cfloat>
+#include <cstdlib>
 
 #include "nbx_internal.cuh"
+#include "nbx_math.cuh"
 
 namespace nbx {
 
@@ -273,15 +275,6 @@ __global__ void __launch_bounds__(256) build_level_kernel(uint32_t first, uint32
 }
 
 // ---- K16 traversal ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float inv_dist3_fast(float d2) {
-  float sq, inv;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(d2));
-  float den = fmaf(d2, sq, FLT_EPSILON);
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(den));
-  return inv;
-}
-__device__ __forceinline__ double inv_dist3_fast(double d2) { return 1.0 / fma(d2, sqrt(d2), DBL_EPSILON); }
-
 // dist2 in the reference's order: ((dx*dx) + dy*dy) + dz*dz with d = xs - xj, no contraction (vec.h:232-240)
 template <typename T, int D>
 __device__ __forceinline__ T dist2_exact(T ax, T ay, T az, T bx, T by, T bz) {
@@ -318,7 +311,7 @@ __global__ void __launch_bounds__(128) bvh_force_kernel(const vec4_t<T>* __restr
         if (bidx < n && bidx != i) {
           vec4_t<T> b = xm[bidx];
           T d2 = dist2_exact<T, D>(xs.x, xs.y, xs.z, b.x, b.y, b.z);
-          T s  = b.w * inv_dist3_fast(d2);
+          T s  = b.w * inv_dist3(d2);
           ax = fma(b.x - xs.x, s, ax);
           ay = fma(b.y - xs.y, s, ay);
           if (D == 3) az = fma(b.z - xs.z, s, az);
@@ -332,7 +325,7 @@ __global__ void __launch_bounds__(128) bvh_force_kernel(const vec4_t<T>* __restr
       const T w          = bw[k];
       const T d2         = dist2_exact<T, D>(xs.x, xs.y, xs.z, nm.x, nm.y, nm.z);
       if (mul_rn(w, w) < mul_rn(theta2, d2)) {  // can_approximate (bvh.h:246-248)
-        T s = nm.w * inv_dist3_fast(d2);
+        T s = nm.w * inv_dist3(d2);
         ax = fma(nm.x - xs.x, s, ax);
         ay = fma(nm.y - xs.y, s, ay);
         if (D == 3) az = fma(nm.z - xs.z, s, az);
@@ -346,6 +339,81 @@ __global__ void __launch_bounds__(128) bvh_force_kernel(const vec4_t<T>* __restr
     }
   }
   a_out[i] = make_v4<T>(mul_rn(c, ax), mul_rn(c, ay), D == 3 ? mul_rn(c, az) : T(0), T(0));
+}
+
+// WARP-COOPERATIVE version of the same walk (used when the leaf offsets fit 27 bits): each lane keeps the reference's
+// per-body state machine — its progress `covered` (= num_covered_particles, bvh.h:267) and the level of the node it wants
+// next; the node index follows from both: k = 2^level - 1 + (covered >> (levels - level)). Every step the warp takes the
+// smallest (covered, level) key over its lanes with one REDUX.MIN, loads THAT node once (warp-uniform address), and only
+// the lanes that asked for it act on it. The warp therefore walks the union of its lanes' paths in leaf order; each lane
+// performs exactly the reference's sequence of tests and interactions.
+template <typename T, int D, bool COUNT = false>
+__global__ void __launch_bounds__(128) bvh_force_warp_kernel(const vec4_t<T>* __restrict__ xm, const vec4_t<T>* __restrict__ node_m,
+                                                             const T* __restrict__ bw, uint32_t n, uint32_t tb, uint32_t te,
+                                                             uint32_t levels, T theta2, T c, vec4_t<T>* __restrict__ a_out,
+                                                             unsigned long long* stats = nullptr) {
+  const uint32_t i     = tb + blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid     = i < te;
+  const vec4_t<T> xs   = xm[valid ? i : tb];
+  unsigned long long n_visit = 0, n_take = 0, n_step = 0;  // COUNT only
+  constexpr uint32_t DONE = 0xffffffffu;
+  uint32_t covered = 0, level = 0;
+  uint32_t key     = valid ? 0u : DONE;  // (covered << 5) | level
+  T ax = 0, ay = 0, az = 0;
+  for (;;) {
+    const uint32_t kmin = __reduce_min_sync(0xffffffffu, key);
+    if (kmin == DONE) break;
+    const uint32_t cl = kmin & 31u, cpos = kmin >> 5;
+    const bool act    = key == kmin;
+    if (COUNT) { n_visit += act; n_step += 1; }
+    if (cl == levels) {  // body level: the two bodies cpos, cpos+1 (bvh.h:288-303)
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const uint32_t bidx = cpos + q;
+        if (bidx < n) {
+          const vec4_t<T> b = xm[bidx];
+          if (act && bidx != i) {
+            T d2 = dist2_exact<T, D>(xs.x, xs.y, xs.z, b.x, b.y, b.z);
+            T s  = b.w * inv_dist3(d2);
+            ax = fma(b.x - xs.x, s, ax);
+            ay = fma(b.y - xs.y, s, ay);
+            if (D == 3) az = fma(b.z - xs.z, s, az);
+          }
+        }
+      }
+      if (act) {
+        covered += 2;
+        level -= 1;
+        if (COUNT) n_take += 1;
+      }
+    } else {
+      const uint32_t k   = ((1u << cl) - 1) + (cpos >> (levels - cl));
+      const vec4_t<T> nm = node_m[k];
+      const T w          = bw[k];
+      if (act) {
+        const T d2 = dist2_exact<T, D>(xs.x, xs.y, xs.z, nm.x, nm.y, nm.z);
+        if (mul_rn(w, w) < mul_rn(theta2, d2)) {
+          T s = nm.w * inv_dist3(d2);
+          ax = fma(nm.x - xs.x, s, ax);
+          ay = fma(nm.y - xs.y, s, ay);
+          if (D == 3) az = fma(nm.z - xs.z, s, az);
+          covered += 1u << (levels - cl);
+          if (COUNT) n_take += 1;
+          if (!(k & 1)) level -= 1;  // right child (or root): continue one level up; left child: sibling, same level
+        } else {
+          level += 1;
+        }
+      }
+    }
+    if (act) key = covered >= n ? DONE : ((covered << 5) | level);
+  }
+  if (COUNT) {
+    atomicAdd(&stats[0], n_visit);
+    atomicAdd(&stats[1], n_take);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&stats[2], n_step);
+    return;
+  }
+  if (valid) a_out[i] = make_v4<T>(mul_rn(c, ax), mul_rn(c, ay), D == 3 ? mul_rn(c, az) : T(0), T(0));
 }
 
 // ---- artefact export ---------------------------------------------------------------------------------------------
@@ -481,9 +549,15 @@ static int force_impl(nbx_engine* e) {
   const uint32_t nt = e->te - e->tb;
   if (nt == 0) return NBX_OK;
   const T theta = T(e->cfg.theta);
-  bvh_force_kernel<T, D><<<(nt + 127) / 128, 128, 0, e->stream>>>(static_cast<const vec4_t<T>*>(e->xm[e->cur]), s->node_m, s->bw, e->n,
-                                                                 e->tb, e->te, s->levels, theta * theta, T(e->cfg.G),
-                                                                 static_cast<vec4_t<T>*>(e->a));
+  static const bool per_thread = [] { const char* v = getenv("NBX_BVH_PER_THREAD"); return v && atoi(v); }();
+  if (s->levels <= 27 && !per_thread)
+    bvh_force_warp_kernel<T, D><<<(nt + 127) / 128, 128, 0, e->stream>>>(static_cast<const vec4_t<T>*>(e->xm[e->cur]), s->node_m, s->bw,
+                                                                        e->n, e->tb, e->te, s->levels, theta * theta, T(e->cfg.G),
+                                                                        static_cast<vec4_t<T>*>(e->a));
+  else
+    bvh_force_kernel<T, D><<<(nt + 127) / 128, 128, 0, e->stream>>>(static_cast<const vec4_t<T>*>(e->xm[e->cur]), s->node_m, s->bw, e->n,
+                                                                   e->tb, e->te, s->levels, theta * theta, T(e->cfg.G),
+                                                                   static_cast<vec4_t<T>*>(e->a));
   e->launches++;
   NBX_CUDA(cudaGetLastError());
   return NBX_OK;
@@ -542,6 +616,22 @@ static int get_nodes_impl(nbx_engine* e, uint64_t* nnodes, void* node_m, void* b
   return rc;
 }
 
+template <typename T, int D>
+static int stats_impl(nbx_engine* e, unsigned long long* dev_stats) {
+  auto* s = st<T>(e);
+  if (!s->built) return fail(NBX_ERR_STATE, "no build_tree has run yet");
+  if (s->levels > 27) return fail(NBX_ERR_INVALID, "traversal stats need n <= 2^27");
+  const uint32_t nt = e->te - e->tb;
+  const T theta     = T(e->cfg.theta);
+  if (nt)
+    bvh_force_warp_kernel<T, D, true><<<(nt + 127) / 128, 128, 0, e->stream>>>(static_cast<const vec4_t<T>*>(e->xm[e->cur]), s->node_m,
+                                                                              s->bw, e->n, e->tb, e->te, s->levels, theta * theta,
+                                                                              T(e->cfg.G), static_cast<vec4_t<T>*>(e->a), dev_stats);
+  e->launches++;
+  NBX_CUDA(cudaGetLastError());
+  return NBX_OK;
+}
+
 #define BVH_DISPATCH(e, fn, ...)                                                          \
   ((e)->prec == 4 ? ((e)->dim == 2 ? fn<float, 2>(__VA_ARGS__) : fn<float, 3>(__VA_ARGS__)) \
                   : ((e)->dim == 2 ? fn<double, 2>(__VA_ARGS__) : fn<double, 3>(__VA_ARGS__)))
@@ -567,6 +657,7 @@ int bvh_compute_force(nbx_engine* e) {
   PhaseTimer pt(e, PH_TRAVERSE);
   return BVH_DISPATCH(e, force_impl, e);
 }
+int bvh_stats(nbx_engine* e, unsigned long long* dev_stats) { return BVH_DISPATCH(e, stats_impl, e, dev_stats); }
 int bvh_get_bbox(nbx_engine* e, void* xmin, void* xmax) { return BVH_DISPATCH(e, get_bbox_impl, e, xmin, xmax); }
 int bvh_get_keys(nbx_engine* e, uint64_t* keys, uint32_t* perm) { return BVH_DISPATCH(e, get_keys_impl, e, keys, perm); }
 int bvh_get_nodes(nbx_engine* e, uint64_t* nnodes, void* node_m, void* bw, void* b) {

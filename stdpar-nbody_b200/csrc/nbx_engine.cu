@@ -394,6 +394,27 @@ int nbx_octree_get_canonical(nbx_engine* e, uint64_t* count, uint32_t* depth, ui
   return octree_get_canonical(e, count, depth, path, kind, monopole);
 }
 
+int nbx_traversal_stats(nbx_engine* e, uint64_t* node_visits, uint64_t* interactions, uint64_t* warp_steps) {
+  NBX_ENTER(e);
+  if (e->algo != NBX_BVH && e->algo != NBX_OCTREE) return fail(NBX_ERR_STATE, "traversal stats need a tree engine");
+  unsigned long long* d = nullptr;
+  NBX_CUDA(cudaMalloc(&d, 3 * sizeof(unsigned long long)));
+  NBX_CUDA(cudaMemsetAsync(d, 0, 3 * sizeof(unsigned long long), e->stream));
+  int rc = e->algo == NBX_BVH ? bvh_stats(e, d) : octree_stats(e, d);
+  unsigned long long h[3] = {0, 0, 0};
+  if (rc == NBX_OK) {
+    cudaError_t err = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    if (err != cudaSuccess) rc = fail(NBX_ERR_CUDA, cudaGetErrorString(err));
+  }
+  cudaFree(d);
+  if (rc != NBX_OK) return rc;
+  if (node_visits) *node_visits = h[0];
+  if (interactions) *interactions = h[1];
+  if (warp_steps) *warp_steps = h[2];
+  return NBX_OK;
+}
+
 int nbx_comm_unique_id(void* id128) { return comm_unique_id(id128); }
 int nbx_comm_init_rank(nbx_engine* e, const void* id128) {
   NBX_ENTER(e);

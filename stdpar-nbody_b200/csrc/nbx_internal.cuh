@@ -148,6 +148,7 @@ int bvh_hilbert_sort(nbx_engine* e);
 int bvh_build_tree(nbx_engine* e);
 int bvh_compute_force(nbx_engine* e);
 int bvh_get_bbox(nbx_engine* e, void* xmin, void* xmax);
+int bvh_stats(nbx_engine* e, unsigned long long* dev_stats);     // counting variant of the walk: {visits, interactions, warp steps}
 int bvh_get_keys(nbx_engine* e, uint64_t* keys, uint32_t* perm);
 int bvh_get_nodes(nbx_engine* e, uint64_t* nnodes, void* node_m, void* bw, void* b);
 // nbx_octree.cu
@@ -155,6 +156,7 @@ int octree_create(nbx_engine* e);
 void octree_destroy(nbx_engine* e);
 int octree_build(nbx_engine* e);
 int octree_compute_force(nbx_engine* e);
+int octree_stats(nbx_engine* e, unsigned long long* dev_stats);
 int octree_check(nbx_engine* e);  // NBX_ERR_CAPACITY if the last build overflowed (syncs the stream)
 int octree_get_root(nbx_engine* e, void* side, void* root_x, uint64_t* nodes_used);
 int octree_get_canonical(nbx_engine* e, uint64_t* count, uint32_t* depth, uint64_t* path, uint32_t* kind,

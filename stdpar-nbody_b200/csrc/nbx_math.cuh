@@ -1,0 +1,56 @@
+// nbx_math.cuh — the softened inverse-distance kernels shared by the force kernels (sm_100a).
+//
+// Seeds come from the XU pipe (MUFU.SQRT / MUFU.RCP for float, MUFU.RSQ64H / MUFU.RCP64H for double, measured on B200:
+// max relative error 2^-20.1 / 2^-20.0 for the double seeds); double results are refined on the FP64 pipe with ONE cubic
+// step each (error^3 => 2^-60, below the rounding of the surrounding operations; measured 1-2 ulp end to end).
+#pragma once
+#include <cfloat>
+
+namespace nbx {
+
+// ---- 1 / (d2^1.5 + eps)   (vec.h:249-252 dist3; all-pairs and bvh) ---------------------------------------------------
+// d2 == 0 gives 1/eps (finite), so a self / coincident pair contributes m * 0 * (1/eps) = 0 exactly as the reference's
+// m*(pj-pi)/dist3 does, without a branch.
+__device__ __forceinline__ float inv_dist3(float d2) {
+  float sq, inv;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(d2));  // MUFU.SQRT
+  float den = fmaf(d2, sq, FLT_EPSILON);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(den));  // MUFU.RCP
+  return inv;
+}
+
+// sqrt(d2) in double: rsqrt seed + cubic step  y1 = y0 (1 + e/2 + 3e^2/8), e = 1 - d2 y0^2 ; sqrt = d2 * y1  (0 -> 0)
+__device__ __forceinline__ double sqrt_fast(double d2) {
+  const double d2c = fmax(d2, 1e-300);
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d2c));  // MUFU.RSQ64H
+  const double t = d2c * y;
+  const double e = fma(-t, y, 1.0);
+  const double q = e * fma(0.375, e, 0.5);
+  y              = fma(y, q, y);
+  return d2 * y;
+}
+// 1/x in double (x > 0): rcp seed + cubic step  r1 = r0 (1 + e + e^2), e = 1 - x r0
+__device__ __forceinline__ double rcp_fast(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));  // MUFU.RCP64H
+  const double e = fma(-x, r, 1.0);
+  return fma(r, fma(e, e, e), r);
+}
+__device__ __forceinline__ double inv_dist3(double d2) { return rcp_fast(fma(d2, sqrt_fast(d2), DBL_EPSILON)); }
+
+// ---- octree form: dx = sqrt(d2) + eps ; 1/dx^3   (vec.h:243-246 dist, octree.h:240-242) ---------------------------------
+__device__ __forceinline__ float dist_eps(float d2) {
+  float sq;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(d2));
+  return sq + FLT_EPSILON;
+}
+__device__ __forceinline__ double dist_eps(double d2) { return sqrt_fast(d2) + DBL_EPSILON; }
+__device__ __forceinline__ float inv_cube(float dx) {
+  float inv;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(dx * dx * dx));
+  return inv;
+}
+__device__ __forceinline__ double inv_cube(double dx) { return rcp_fast(dx * dx * dx); }
+
+}  // namespace nbx

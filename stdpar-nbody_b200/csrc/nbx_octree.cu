@@ -20,6 +20,7 @@
 #include <cfloat>
 
 #include "nbx_internal.cuh"
+#include "nbx_math.cuh"
 
 namespace nbx {
 
@@ -366,67 +367,60 @@ __global__ void __launch_bounds__(256) monopole_level_kernel(const uint32_t* __r
 
 // ---- K9 traversal ---------------------------------------------------------------------------------------------------
 // octree.h:227-255: dx = sqrt(dist2)+eps ; accept when leaf or side/dx < theta ; a += m*(xj-x)/dx^3.
-template <typename T>
-struct WalkMath;
-template <>
-struct WalkMath<float> {
-  static __device__ __forceinline__ float dist(float d2) {
-    float sq;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(d2));
-    return sq + FLT_EPSILON;
-  }
-  static __device__ __forceinline__ bool accept(float side, float dx, float theta) { return side < theta * dx; }
-  static __device__ __forceinline__ float inv_cube(float dx) {
-    float inv;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(dx * dx * dx));
-    return inv;
-  }
-  static __device__ __forceinline__ float side_at(float root_side, uint32_t depth) {
-    return root_side * __int_as_float(int(127 - depth) << 23);  // exact halvings
-  }
-};
-template <>
-struct WalkMath<double> {
-  static __device__ __forceinline__ double dist(double d2) { return sqrt(d2) + DBL_EPSILON; }
-  static __device__ __forceinline__ bool accept(double side, double dx, double theta) { return side / dx < theta; }
-  static __device__ __forceinline__ double inv_cube(double dx) { return 1.0 / (dx * dx * dx); }
-  static __device__ __forceinline__ double side_at(double root_side, uint32_t depth) {
-    return root_side * __longlong_as_double((long long)(1023 - depth) << 52);
-  }
-};
+// The test is evaluated as side < theta*dx (dx > 0): it can only differ from the reference's division when side/dx is
+// within one rounding of theta.
+// exact halvings of the root side: side(depth) = root_side * 2^-depth
+__device__ __forceinline__ float side_at(float root_side, uint32_t depth) { return root_side * __int_as_float(int(127 - depth) << 23); }
+__device__ __forceinline__ double side_at(double root_side, uint32_t depth) {
+  return root_side * __longlong_as_double((long long)(1023 - depth) << 52);
+}
 
-// One thread per SORTED slot t (body perm[t]): neighbouring lanes are neighbours along the tree's DFS order and read the
-// same records most of the time. The result goes to a_sorted[t].
-template <typename T, int D>
+// WARP-COOPERATIVE walk: one lane per SORTED slot t (body perm[t]); the 32 lanes of a warp are neighbours along the
+// tree's DFS order. The warp walks the UNION of its lanes' paths with ONE position `p` (warp-uniform => every record
+// load is a single broadcast sector instead of up to 32 divergent ones), while each lane keeps the reference's per-body
+// semantics exactly: a lane that accepts node p while another lane needs it opened simply sleeps until the walk leaves
+// that subtree (`resume` = the record index where it wakes up). Interaction sets are identical to the per-body walk.
+template <typename T, int D, bool COUNT = false>
 __global__ void __launch_bounds__(128) octree_force_kernel(const vec4_t<T>* __restrict__ mono, const uint2* __restrict__ meta,
                                                            const Root<T>* __restrict__ root, const uint32_t* __restrict__ cell_base,
                                                            uint32_t n, uint32_t tb, uint32_t te, T theta, T c,
-                                                           vec4_t<T>* __restrict__ a_sorted) {
-  const uint32_t t = tb + blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= te) return;
-  const uint32_t nrec  = n + root->cells;
-  const T root_side    = root->side;
-  const vec4_t<T> xs   = mono[t + cell_base[t + 1]];  // own leaf record = own position
+                                                           vec4_t<T>* __restrict__ a_sorted, unsigned long long* stats = nullptr) {
+  unsigned long long n_visit = 0, n_take = 0, n_step = 0;  // COUNT only
+  const uint32_t t    = tb + blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid    = t < te;
+  const uint32_t nrec = n + root->cells;
+  const T root_side   = root->side;
+  const uint32_t tt   = valid ? t : tb;
+  const vec4_t<T> xs  = mono[tt + cell_base[tt + 1]];  // own leaf record = own position
   T ax = 0, ay = 0, az = 0;
-  uint32_t p = 0;
+  uint32_t resume = valid ? 0u : 0xffffffffu;  // first record this lane still has to look at
+  uint32_t p      = 0;
   while (p < nrec) {
-    const vec4_t<T> nm = mono[p];
+    const vec4_t<T> nm = mono[p];  // warp-uniform address
     const uint2 me     = meta[p];
     const T dx_ = nm.x - xs.x, dy_ = nm.y - xs.y, dz_ = D == 3 ? nm.z - xs.z : T(0);
     T d2 = fma(dy_, dy_, dx_ * dx_);
     if (D == 3) d2 = fma(dz_, dz_, d2);
-    const T dx = WalkMath<T>::dist(d2);
-    if ((me.y & LEAF_FLAG) || WalkMath<T>::accept(WalkMath<T>::side_at(root_side, me.y & 0xff), dx, theta)) {
-      const T s = nm.w * WalkMath<T>::inv_cube(dx);
+    const T dx      = dist_eps(d2);
+    const bool act  = p >= resume;
+    const bool take = (me.y & LEAF_FLAG) || (side_at(root_side, me.y & 0xff) < theta * dx);
+    if (COUNT) { n_visit += act; n_take += act && take; n_step += 1; }
+    if (act && take) {
+      const T s = nm.w * inv_cube(dx);
       ax = fma(dx_, s, ax);
       ay = fma(dy_, s, ay);
       if (D == 3) az = fma(dz_, s, az);
-      p = me.x;
-    } else {
-      p = p + 1;
+      resume = me.x;
     }
+    p = __any_sync(0xffffffffu, act && !take) ? p + 1 : me.x;
   }
-  a_sorted[t] = make_v4<T>(c * ax, c * ay, D == 3 ? c * az : T(0), T(0));
+  if (COUNT) {
+    atomicAdd(&stats[0], n_visit);
+    atomicAdd(&stats[1], n_take);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&stats[2], n_step);
+    return;
+  }
+  if (valid) a_sorted[t] = make_v4<T>(c * ax, c * ay, D == 3 ? c * az : T(0), T(0));
 }
 
 // a[perm[t]] = a_sorted[t]
@@ -640,6 +634,19 @@ static int get_canonical_impl(nbx_engine* e, uint64_t* count, uint32_t* depth, u
   return NBX_OK;
 }
 
+template <typename T, int D>
+static int stats_impl(nbx_engine* e, unsigned long long* dev_stats) {
+  auto* s = st<T>(e);
+  if (!s->built) return fail(NBX_ERR_STATE, "no octree build has run yet");
+  const uint32_t nt = e->te - e->tb;
+  if (nt)
+    octree_force_kernel<T, D, true><<<(nt + 127) / 128, 128, 0, e->stream>>>(s->mono, s->meta, s->root, s->cnt, e->n, e->tb, e->te,
+                                                                            T(e->cfg.theta), T(e->cfg.G), s->a_sorted, dev_stats);
+  e->launches++;
+  NBX_CUDA(cudaGetLastError());
+  return NBX_OK;
+}
+
 #define OCT_DISPATCH(e, fn, ...)                                                          \
   ((e)->prec == 4 ? ((e)->dim == 2 ? fn<float, 2>(__VA_ARGS__) : fn<float, 3>(__VA_ARGS__)) \
                   : ((e)->dim == 2 ? fn<double, 2>(__VA_ARGS__) : fn<double, 3>(__VA_ARGS__)))
@@ -652,6 +659,7 @@ void octree_destroy(nbx_engine* e) {
 int octree_build(nbx_engine* e) { return OCT_DISPATCH(e, build_impl, e); }
 int octree_compute_force(nbx_engine* e) { return OCT_DISPATCH(e, force_impl, e); }
 int octree_check(nbx_engine* e) { return OCT_DISPATCH(e, check_overflow, e); }
+int octree_stats(nbx_engine* e, unsigned long long* dev_stats) { return OCT_DISPATCH(e, stats_impl, e, dev_stats); }
 int octree_get_root(nbx_engine* e, void* side, void* root_x, uint64_t* nodes_used) {
   return OCT_DISPATCH(e, get_root_impl, e, side, root_x, nodes_used);
 }

@@ -30,7 +30,7 @@ SYMBOLS = [
     "nbx_accelerate_step", "nbx_calc_energies", "nbx_bvh_bounding_box", "nbx_bvh_hilbert_sort", "nbx_bvh_build_tree",
     "nbx_bvh_compute_force", "nbx_bvh_get_keys", "nbx_bvh_get_nodes", "nbx_octree_build", "nbx_octree_compute_force",
     "nbx_octree_get_root", "nbx_octree_get_canonical", "nbx_comm_unique_id", "nbx_comm_init_rank",
-    "nbx_measure_fma_peak", "nbx_get_counters", "nbx_set_phase_timing", "nbx_get_phase_ms",
+    "nbx_measure_fma_peak", "nbx_traversal_stats", "nbx_get_counters", "nbx_set_phase_timing", "nbx_get_phase_ms",
 ]
 
 
@@ -225,6 +225,11 @@ class Engine:
         k, h, d = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
         _check(lib().nbx_get_counters(self._h, C.byref(k), C.byref(h), C.byref(d)))
         return dict(kernel_launches=k.value, h2d_bytes=h.value, d2h_bytes=d.value)
+
+    def traversal_stats(self):
+        v, a, w = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        _check(lib().nbx_traversal_stats(self._h, C.byref(v), C.byref(a), C.byref(w)))
+        return dict(node_visits=v.value, interactions=a.value, warp_steps=w.value)
 
     def set_phase_timing(self, enable=True):
         _check(lib().nbx_set_phase_timing(self._h, C.c_int(1 if enable else 0)))

@@ -145,3 +145,18 @@ def test_sort_properties_10M():
     eq = ks[1:] == ks[:-1]
     assert (perm[1:][eq] > perm[:-1][eq]).all()
     assert same(xs, x[perm])
+
+
+def test_traversal_stats_match_oracle_visits(oracle_fast):
+    """The warp-cooperative walk performs, per body, exactly the reference's sequence of node tests: the (body, node)
+    test count equals the oracle's loop-iteration count."""
+    s = oracle_fast.galaxy(20000, np.float64, 3)
+    lo, hi = oracle_fast.bbox(s["x"])
+    so = oracle_fast.permute(oracle_fast.sort_perm(oracle_fast.keys(s["x"], lo, hi)), s)
+    nm, bw, _ = oracle_fast.bvh_build(so["m"], so["x"])
+    _, visits = oracle_fast.bvh_force(so["m"], so["x"], nm, bw, s["G"], THETA)
+    with engine(s) as e:
+        e.bounding_box(); e.hilbert_sort(); e.build_tree()
+        st = e.traversal_stats()
+    assert st["node_visits"] == visits
+    assert st["warp_steps"] * 32 >= st["node_visits"] and st["interactions"] <= st["node_visits"]
