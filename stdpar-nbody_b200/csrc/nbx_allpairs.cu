@@ -17,107 +17,9 @@
 
 #include "nbx_internal.cuh"
 #include "nbx_math.cuh"
+#include "nbx_device.cuh"
 
 namespace nbx {
-
-// One-MUFU variant used for a fraction of the float pairs (see all_pairs_kernel, NB): with q = rsqrt(d2)^3 = 1/d2^1.5,
-//   m/(d2^1.5 + eps) = m*q/(1 + eps*q) = m*q*(1 - u + u^2 - ...),  u = eps*q.
-// The first-order form m*q*(1-u) is exact to u^2 <= 2^-24 while q <= Q_CAP = 2^-12/eps = 2048 (pairs farther apart than
-// 0.079); `qmax` records the largest q seen so that the caller can redo the (rare) tiles that contain a closer pair — or
-// the self pair, whose q is +inf — with the exact two-MUFU formula. XU work per pair drops from 2 to 1 MUFU at the price
-// of 3 more FMA-pipe instructions and one FMNMX.
-constexpr float AP_Q_CAP = 2048.0f;
-__device__ __forceinline__ float scaled_inv_dist3_rsq(float d2, float m, float& qmax) {
-  float r;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d2));  // MUFU.RSQ
-  const float q = (r * r) * r;
-  qmax          = fmaxf(qmax, q);
-  const float mq = m * q;
-  const float u  = q * FLT_EPSILON;
-  return fmaf(-u, mq, mq);
-}
-__device__ __forceinline__ double scaled_inv_dist3_rsq(double d2, double m, double&) { return m * inv_dist3(d2); }
-
-// round-to-nearest ops that the compiler may not contract: the leapfrog restates system.h:56-58 operation by
-// operation so that, given the same `a`, it is bit-identical to the pinned (-ffp-contract=off) reference.
-__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
-
-// ---- TMA bulk copy + mbarrier helpers (PTX) -------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-// 1-D bulk async copy global -> shared, completion signalled on `bar` (SASS: UBLKCP)
-__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-// L2-only (cache-global) vec4 accesses for data produced by other CTAs of the same launch
-__device__ __forceinline__ float4 ldcg_v4(const float4* p) { return __ldcg(p); }
-__device__ __forceinline__ double4 ldcg_v4(const double4* p) {
-  double2 lo = __ldcg(reinterpret_cast<const double2*>(p));
-  double2 hi = __ldcg(reinterpret_cast<const double2*>(p) + 1);
-  return make_double4(lo.x, lo.y, hi.x, hi.y);
-}
-__device__ __forceinline__ void stcg_v4(float4* p, float4 v) { __stcg(p, v); }
-__device__ __forceinline__ void stcg_v4(double4* p, double4 v) {
-  __stcg(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
-  __stcg(reinterpret_cast<double2*>(p) + 1, make_double2(v.z, v.w));
-}
-
-// ---- leapfrog (system.h:52-60) --------------------------------------------------------------------------------
-template <typename T>
-struct LeapArgs {
-  const vec4_t<T>* xm_in;
-  vec4_t<T>* xm_out;
-  vec4_t<T>* v;
-  vec4_t<T>* a;
-  vec4_t<T>* ao;
-  T dt;
-};
-
-// x += dt*v + 0.5*dt*dt*ao ; v += 0.5*dt*(a+ao) ; ao = a     (all vec ops componentwise, same association)
-template <typename T, int D>
-__device__ __forceinline__ void leapfrog_body(const LeapArgs<T>& p, uint32_t i, vec4_t<T> anew) {
-  vec4_t<T> xm = p.xm_in[i];
-  vec4_t<T> v  = p.v[i];
-  vec4_t<T> ao = p.ao[i];
-  const T hdt2 = mul_rn(mul_rn(T(0.5), p.dt), p.dt);
-  const T hdt  = mul_rn(T(0.5), p.dt);
-  xm.x = add_rn(xm.x, add_rn(mul_rn(v.x, p.dt), mul_rn(ao.x, hdt2)));
-  xm.y = add_rn(xm.y, add_rn(mul_rn(v.y, p.dt), mul_rn(ao.y, hdt2)));
-  if (D == 3) xm.z = add_rn(xm.z, add_rn(mul_rn(v.z, p.dt), mul_rn(ao.z, hdt2)));
-  v.x = add_rn(v.x, mul_rn(add_rn(anew.x, ao.x), hdt));
-  v.y = add_rn(v.y, mul_rn(add_rn(anew.y, ao.y), hdt));
-  if (D == 3) v.z = add_rn(v.z, mul_rn(add_rn(anew.z, ao.z), hdt));
-  p.xm_out[i] = xm;
-  p.v[i]      = v;
-  p.ao[i]     = anew;
-}
 
 template <typename T, int D>
 __global__ void accelerate_kernel(LeapArgs<T> p, uint32_t tb, uint32_t te) {
@@ -142,9 +44,8 @@ struct AllPairsArgs {
   LeapArgs<T> leap;      // leap.a is also the destination of the acceleration
 };
 
-template <typename T, int D, int TI, int BLOCK, int TILE, int STAGES, int MINB, int NB, int UNROLL = 4>
+template <typename T, int D, int TI, int BLOCK, int TILE, int STAGES, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) all_pairs_kernel(AllPairsArgs<T> p) {
-  static_assert(NB >= 0 && NB < TI || NB == 0, "NB targets of each thread use the one-MUFU path");
   using V4 = vec4_t<T>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   V4* tiles      = reinterpret_cast<V4*>(smem_raw);
@@ -186,12 +87,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) all_pairs_kernel(AllPairsArgs<T> 
     const int stage = k % STAGES;
     mbar_wait(&bars[stage], (k / STAGES) & 1);
     const V4* tile = tiles + size_t(stage) * TILE;
-    // snapshot of the accumulators of the NB one-MUFU targets, restored if this tile has to be redone exactly
-    T sx[NB ? NB : 1], sy[NB ? NB : 1], sz[NB ? NB : 1];
-    T qmax = T(0);
-#pragma unroll
-    for (int t = 0; t < NB; ++t) { sx[t] = ax[TI - NB + t]; sy[t] = ay[TI - NB + t]; sz[t] = az[TI - NB + t]; }
-#pragma unroll UNROLL
+#pragma unroll 4
     for (int j = 0; j < TILE; ++j) {
       const V4 b = tile[j];  // broadcast LDS.128 (2x for double)
 #pragma unroll
@@ -204,33 +100,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) all_pairs_kernel(AllPairsArgs<T> 
           dz = b.z - zi[t];
           d2 = fma(dz, dz, d2);
         }
-        T s   = t < TI - NB ? b.w * inv_dist3(d2) : scaled_inv_dist3_rsq(d2, b.w, qmax);
+        T s   = b.w * inv_dist3(d2);
         ax[t] = fma(dx, s, ax[t]);
         ay[t] = fma(dy, s, ay[t]);
         if (D == 3) az[t] = fma(dz, s, az[t]);
-      }
-    }
-    if (NB > 0 && !(qmax <= T(AP_Q_CAP))) {  // a close (or the self) pair in this tile: redo it with the exact formula
-#pragma unroll
-      for (int t = 0; t < NB; ++t) { ax[TI - NB + t] = sx[t]; ay[TI - NB + t] = sy[t]; az[TI - NB + t] = sz[t]; }
-#pragma unroll 2
-      for (int j = 0; j < TILE; ++j) {
-        const V4 b = tile[j];
-#pragma unroll
-        for (int t = TI - NB; t < TI; ++t) {
-          T dx = b.x - xi[t];
-          T dy = b.y - yi[t];
-          T d2 = fma(dy, dy, dx * dx);
-          T dz = T(0);
-          if (D == 3) {
-            dz = b.z - zi[t];
-            d2 = fma(dz, dz, d2);
-          }
-          T s   = b.w * inv_dist3(d2);
-          ax[t] = fma(dx, s, ax[t]);
-          ay[t] = fma(dy, s, ay[t]);
-          if (D == 3) az[t] = fma(dz, s, az[t]);
-        }
       }
     }
     __syncthreads();  // every warp is done with this stage: safe to overwrite it
@@ -480,9 +353,9 @@ static LeapArgs<T> make_leap(nbx_engine* e, bool to_next) {
 constexpr int AP_TILE   = 512;  // bodies per shared-memory tile (also the zero-mass padding appended to xm)
 constexpr int AP_STAGES = 4;
 
-template <typename T, int D, int TI, int BLOCK, int MINB, int NB = 0, int UNROLL = 4>
+template <typename T, int D, int TI, int BLOCK, int MINB>
 static int launch_all_pairs_cfg(nbx_engine* e, bool fuse, uint32_t nsplit, uint32_t tiles_per_split) {
-  auto kern = all_pairs_kernel<T, D, TI, BLOCK, AP_TILE, AP_STAGES, MINB, NB, UNROLL>;
+  auto kern = all_pairs_kernel<T, D, TI, BLOCK, AP_TILE, AP_STAGES, MINB>;
   const size_t smem = size_t(AP_STAGES) * AP_TILE * sizeof(vec4_t<T>) + AP_STAGES * sizeof(uint64_t);
   static bool attr_done = false;  // per template instantiation
   if (!attr_done) {
@@ -534,10 +407,7 @@ static int launch_all_pairs(nbx_engine* e, bool fuse) {
   const uint32_t tiles_total = (e->n + AP_TILE - 1) / AP_TILE;
   // pick the target register blocking so that small problems still fill the chip
   constexpr int TI_MAX = sizeof(T) == 4 ? 4 : 2;
-  static const int var = [] { const char* v = getenv("NBX_AP_VAR"); return v ? atoi(v) : 0; }();
   int ti               = TI_MAX;
-  if (sizeof(T) == 4 && (var == 3 || var == 4)) ti = 2;
-  if (sizeof(T) == 4 && var == 5) ti = 8;
   const uint32_t want  = uint32_t(e->sm_count) * 4;
   while (ti > 1 && ((nt + 256 * ti - 1) / (256 * ti)) * tiles_total < want * 4) ti >>= 1;
   const int block        = 256;
@@ -551,16 +421,6 @@ static int launch_all_pairs(nbx_engine* e, bool fuse) {
   uint32_t tps = (tiles_total + nsplit - 1) / nsplit;
   nsplit       = (tiles_total + tps - 1) / tps;
   if constexpr (sizeof(T) == 4) {
-    static const int mix = [] { const char* v = getenv("NBX_AP_MIX"); return v ? atoi(v) : 0; }();
-    if (var == 1 && ti == 4) return launch_all_pairs_cfg<T, D, 4, 256, 3, 0, 8>(e, fuse, nsplit, tps);
-    if (var == 2 && ti == 4) return launch_all_pairs_cfg<T, D, 4, 256, 4, 0, 4>(e, fuse, nsplit, tps);
-    if (var == 3 && ti == 2) return launch_all_pairs_cfg<T, D, 2, 256, 4, 0, 8>(e, fuse, nsplit, tps);
-    if (var == 4 && ti == 2) return launch_all_pairs_cfg<T, D, 2, 256, 6, 0, 4>(e, fuse, nsplit, tps);
-    if (var == 5 && ti == 8) return launch_all_pairs_cfg<T, D, 8, 256, 2, 0, 2>(e, fuse, nsplit, tps);
-    if (var == 6 && ti == 4) return launch_all_pairs_cfg<T, D, 4, 256, 3, 0, 2>(e, fuse, nsplit, tps);
-    if (var == 7 && ti == 4) return launch_all_pairs_cfg<T, D, 4, 256, 3, 2, 8>(e, fuse, nsplit, tps);
-    if (ti == 4 && mix == 1) return launch_all_pairs_cfg<T, D, 4, 256, 3, 1>(e, fuse, nsplit, tps);
-    if (ti == 4 && mix == 2) return launch_all_pairs_cfg<T, D, 4, 256, 3, 2>(e, fuse, nsplit, tps);
     if (ti == 4) return launch_all_pairs_cfg<T, D, 4, 256, 3>(e, fuse, nsplit, tps);
     if (ti == 2) return launch_all_pairs_cfg<T, D, 2, 256, 3>(e, fuse, nsplit, tps);
     return launch_all_pairs_cfg<T, D, 1, 256, 3>(e, fuse, nsplit, tps);
@@ -573,6 +433,11 @@ static int launch_all_pairs(nbx_engine* e, bool fuse) {
 int all_pairs_force(nbx_engine* e, bool fuse_integrate) {
   PhaseTimer pt(e, PH_FORCE);
   int rc;
+  if (all_pairs_sym_enabled(e)) {
+    rc = all_pairs_sym_force(e, fuse_integrate);
+    if (rc == NBX_OK && fuse_integrate) e->cur ^= 1;
+    return rc;
+  }
   if (e->prec == 4) rc = e->dim == 2 ? launch_all_pairs<float, 2>(e, fuse_integrate) : launch_all_pairs<float, 3>(e, fuse_integrate);
   else rc = e->dim == 2 ? launch_all_pairs<double, 2>(e, fuse_integrate) : launch_all_pairs<double, 3>(e, fuse_integrate);
   if (rc == NBX_OK && fuse_integrate) e->cur ^= 1;
@@ -634,11 +499,12 @@ int accelerate_range(nbx_engine* e, uint32_t tb, uint32_t te) {
   return e->dim == 2 ? launch_accelerate<double, 2>(e, tb, te) : launch_accelerate<double, 3>(e, tb, te);
 }
 
-// Trees keep the whole state replicated on every rank (accelerations are all-gathered), so they integrate all bodies;
-// the all-pairs variants integrate their own targets and all-gather the new positions.
+// Trees and the symmetric all-pairs keep the whole state replicated on every rank (accelerations are all-gathered /
+// all-reduced), so they integrate all bodies; the ordered all-pairs variants integrate their own targets and all-gather
+// the new positions.
 int accelerate_step(nbx_engine* e) {
-  const bool tree = e->algo == NBX_BVH || e->algo == NBX_OCTREE;
-  return tree ? accelerate_range(e, 0, e->n) : accelerate_range(e, e->tb, e->te);
+  const bool replicated = e->algo == NBX_BVH || e->algo == NBX_OCTREE || all_pairs_sym_enabled(e);
+  return replicated ? accelerate_range(e, 0, e->n) : accelerate_range(e, e->tb, e->te);
 }
 
 template <typename T, int D>

@@ -1,0 +1,317 @@
+// nbx_allpairs_sym.cu — all-pairs force with Newton's third law (each unordered pair evaluated once), sm_100a.
+//
+// The reference's all_pairs_force (src/all_pairs.h:14-27) evaluates every ORDERED pair; its own TODO
+// (src/all_pairs.h:41-42) notes that the symmetry of the force pairs halves the work. Every pair term is exactly
+// antisymmetric in floating point ((xj-xi) == -(xi-xj), same d2), so evaluating it once and applying it to both bodies
+// changes nothing but the summation order. The pair kernel is bound by instruction dispatch (11 FMA-pipe + 2 MUFU per
+// ordered pair); sharing dx,dy,dz,d2,sqrt,rcp between the two directions costs 15 FMA-pipe + 2 MUFU per
+// UNORDERED pair, i.e. ~1.5x fewer issue cycles per ordered pair.
+//
+// Decomposition (deterministic, no atomics): bodies are cut into K blocks of B bodies (K <= 256). A CTA owns one unit
+// (I, J), I <= J: it sweeps the J block through shared memory (TMA bulk copies, 256-body tiles) once per 256*RI-body
+// sub-block of I. "Action" sums (on i in I) live in registers over the whole sweep; "reaction" partials (on j in J) are
+// reduced across the warp with a transposed shuffle butterfly every 4 bodies, across the 8 warps through shared memory
+// every tile, and accumulated by the CTA — the only writer — into P[I][j]. Actions go to P[J][i]. Diagonal units
+// (I == J) evaluate ordered pairs without reaction. Afterwards a[b] = c * sum_K P[K][b] in fixed K order, fused with
+// the leapfrog update. Every P entry has exactly one writer and every sum a fixed order => bit-reproducible.
+// Multi-GPU: units are dealt round-robin to the ranks, the per-rank sums are combined with one ncclAllReduce of the
+// accelerations and every rank integrates all bodies (replicated state, no position exchange).
+#include <cfloat>
+
+#include "nbx_device.cuh"
+#include "nbx_internal.cuh"
+#include "nbx_math.cuh"
+
+namespace nbx {
+
+namespace {
+
+constexpr int SYM_JT     = 256;  // bodies per shared-memory tile
+constexpr int SYM_STAGES = 4;
+constexpr int SYM_WARPS  = 8;
+
+template <typename T>
+struct SymArgs {
+  const vec4_t<T>* xm;
+  vec4_t<T>* P;       // [K][slab]
+  uint64_t slab;      // K * B (bodies, padded)
+  uint32_t B, K;
+  uint32_t unit_begin, unit_stride;
+};
+
+__device__ __forceinline__ void unit_to_blocks(uint32_t u, uint32_t& I, uint32_t& J) {
+  // u = J*(J+1)/2 + I, 0 <= I <= J
+  uint32_t j = uint32_t((sqrt(8.0 * double(u) + 1.0) - 1.0) * 0.5);
+  while (uint64_t(j + 1) * (j + 2) / 2 <= u) ++j;
+  while (uint64_t(j) * (j + 1) / 2 > u) --j;
+  J = j;
+  I = u - uint32_t(uint64_t(j) * (j + 1) / 2);
+}
+
+template <typename T, int D, int RI, int MINB>
+__global__ void __launch_bounds__(256, MINB) all_pairs_sym_kernel(SymArgs<T> p) {
+  using V4 = vec4_t<T>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  V4* tiles      = reinterpret_cast<V4*>(smem_raw);
+  T* racc        = reinterpret_cast<T*>(smem_raw + size_t(SYM_STAGES) * SYM_JT * sizeof(V4));  // [warp][j][3]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + size_t(SYM_STAGES) * SYM_JT * sizeof(V4) + size_t(SYM_WARPS) * SYM_JT * 3 * sizeof(T));
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t I, J;
+  unit_to_blocks(p.unit_begin + blockIdx.x * p.unit_stride, I, J);
+  const bool diag     = I == J;
+  const uint32_t I0   = I * p.B, J0 = J * p.B;
+  const uint32_t nsub = p.B / (256 * RI), ntile = p.B / SYM_JT;
+  const int total     = int(nsub * ntile);
+  constexpr uint32_t TILE_BYTES = SYM_JT * sizeof(V4);
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < SYM_STAGES; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&](int k) {  // k-th tile of the CTA's (isub, jt) sequence: the J block is re-swept for every sub-block of I
+    const int stage = k % SYM_STAGES;
+    mbar_expect_tx(&bars[stage], TILE_BYTES);
+    tma_load_1d(tiles + size_t(stage) * SYM_JT, p.xm + size_t(J0) + size_t(k % int(ntile)) * SYM_JT, TILE_BYTES, &bars[stage]);
+  };
+  if (tid == 0)
+    for (int k = 0; k < SYM_STAGES && k < total; ++k) issue(k);
+
+  V4* Paction = p.P + uint64_t(J) * p.slab;  // actions on i in I caused by block J
+  V4* Preact  = p.P + uint64_t(I) * p.slab;  // reactions on j in J caused by block I
+
+  int k = 0;
+  for (uint32_t isub = 0; isub < nsub; ++isub) {
+    T xi[RI], yi[RI], zi[RI], mi[RI], ax[RI], ay[RI], az[RI];
+#pragma unroll
+    for (int t = 0; t < RI; ++t) {
+      const V4 b = p.xm[I0 + isub * (256 * RI) + t * 256 + tid];
+      xi[t] = b.x; yi[t] = b.y; zi[t] = b.z; mi[t] = b.w;
+      ax[t] = ay[t] = az[t] = T(0);
+    }
+    for (uint32_t jt = 0; jt < ntile; ++jt, ++k) {
+      const int stage = k % SYM_STAGES;
+      mbar_wait(&bars[stage], (k / SYM_STAGES) & 1);
+      const V4* tile = tiles + size_t(stage) * SYM_JT;
+      if (diag) {
+#pragma unroll 4
+        for (int j = 0; j < SYM_JT; ++j) {
+          const V4 b = tile[j];
+#pragma unroll
+          for (int t = 0; t < RI; ++t) {
+            T dx = b.x - xi[t], dy = b.y - yi[t];
+            T d2 = fma(dy, dy, dx * dx);
+            T dz = T(0);
+            if (D == 3) { dz = b.z - zi[t]; d2 = fma(dz, dz, d2); }
+            T s   = b.w * inv_dist3(d2);
+            ax[t] = fma(dx, s, ax[t]);
+            ay[t] = fma(dy, s, ay[t]);
+            if (D == 3) az[t] = fma(dz, s, az[t]);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int j0 = 0; j0 < SYM_JT; j0 += 4) {
+          T v[12];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const V4 b = tile[j0 + jj];
+            T rx = T(0), ry = T(0), rz = T(0);
+#pragma unroll
+            for (int t = 0; t < RI; ++t) {
+              T dx = b.x - xi[t], dy = b.y - yi[t];
+              T d2 = fma(dy, dy, dx * dx);
+              T dz = T(0);
+              if (D == 3) { dz = b.z - zi[t]; d2 = fma(dz, dz, d2); }
+              const T inv = inv_dist3(d2);
+              const T si = b.w * inv, sj = mi[t] * inv;
+              ax[t] = fma(dx, si, ax[t]);
+              ay[t] = fma(dy, si, ay[t]);
+              if (D == 3) az[t] = fma(dz, si, az[t]);
+              rx = fma(-dx, sj, rx);
+              ry = fma(-dy, sj, ry);
+              if (D == 3) rz = fma(-dz, sj, rz);
+            }
+            v[3 * jj] = rx; v[3 * jj + 1] = ry; v[3 * jj + 2] = rz;
+          }
+          // transposed butterfly over the warp: 12 values -> 6 -> 3 per lane, then three plain stages; lanes 0, 8, 16, 24
+          // end up with the warp totals of bodies j0+0, j0+1, j0+2, j0+3 (fixed order => deterministic)
+          T w[6], u[3];
+          const bool hi16 = lane & 16, hi8 = lane & 8;
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+            const T mine = hi16 ? v[6 + q] : v[q];
+            const T send = hi16 ? v[q] : v[6 + q];
+            w[q] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
+          }
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const T mine = hi8 ? w[3 + q] : w[q];
+            const T send = hi8 ? w[q] : w[3 + q];
+            u[q] = mine + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            u[q] += __shfl_xor_sync(0xffffffffu, u[q], 4);
+            u[q] += __shfl_xor_sync(0xffffffffu, u[q], 2);
+            u[q] += __shfl_xor_sync(0xffffffffu, u[q], 1);
+          }
+          if ((lane & 7) == 0) {
+            const int jsel = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+            T* dst = racc + (size_t(warp) * SYM_JT + j0 + jsel) * 3;
+            dst[0] = u[0]; dst[1] = u[1]; dst[2] = u[2];
+          }
+        }
+        __syncthreads();
+        {  // the CTA is the only writer of P[I][j in J]: accumulate over the sub-blocks of I in order
+          T rx = T(0), ry = T(0), rz = T(0);
+#pragma unroll
+          for (int wq = 0; wq < SYM_WARPS; ++wq) {
+            const T* src = racc + (size_t(wq) * SYM_JT + tid) * 3;
+            rx += src[0]; ry += src[1]; rz += src[2];
+          }
+          V4* dst = Preact + J0 + jt * SYM_JT + tid;
+          if (isub != 0) {
+            const V4 old = ldcg_v4(dst);
+            rx += old.x; ry += old.y; rz += old.z;
+          }
+          stcg_v4(dst, make_v4<T>(rx, ry, rz, T(0)));
+        }
+      }
+      __syncthreads();  // tile (and racc) free again
+      if (tid == 0 && k + SYM_STAGES < total) issue(k + SYM_STAGES);
+    }
+#pragma unroll
+    for (int t = 0; t < RI; ++t)
+      stcg_v4(Paction + I0 + isub * (256 * RI) + t * 256 + tid, make_v4<T>(ax[t], ay[t], az[t], T(0)));
+  }
+}
+
+// a[b] = c * sum_K P[K][b] (K ascending, only the units this rank computed), optionally fused with the leapfrog
+template <typename T, int D>
+__global__ void __launch_bounds__(256) sym_reduce_kernel(const vec4_t<T>* __restrict__ P, uint64_t slab, uint32_t B, uint32_t K, uint32_t n,
+                                                         uint32_t unit_begin, uint32_t unit_stride, T c, int finish, int fuse,
+                                                         vec4_t<T>* __restrict__ asum, LeapArgs<T> leap) {
+  const uint32_t b = blockIdx.x * 256 + threadIdx.x;
+  if (b >= n) return;
+  const uint32_t Bb = (blockIdx.x * 256) / B;  // B is a multiple of 256: uniform per CTA
+  T sx = 0, sy = 0, sz = 0;
+  for (uint32_t k = 0; k < K; ++k) {
+    const uint32_t lo = k < Bb ? k : Bb, hi = k < Bb ? Bb : k;
+    const uint32_t u  = uint32_t(uint64_t(hi) * (hi + 1) / 2) + lo;
+    if (u < unit_begin || (u - unit_begin) % unit_stride) continue;  // another rank's unit
+    const vec4_t<T> q = ldcg_v4(P + uint64_t(k) * slab + b);
+    sx += q.x; sy += q.y; sz += q.z;
+  }
+  if (!finish) {
+    asum[b] = make_v4<T>(sx, sy, D == 3 ? sz : T(0), T(0));
+    return;
+  }
+  const vec4_t<T> anew = make_v4<T>(mul_rn(sx, c), mul_rn(sy, c), D == 3 ? mul_rn(sz, c) : T(0), T(0));
+  leap.a[b] = anew;
+  if (fuse) leapfrog_body<T, D>(leap, b, anew);
+}
+
+// after the all-reduce of the unscaled sums: scale by c, (optionally) leapfrog
+template <typename T, int D>
+__global__ void __launch_bounds__(256) sym_finish_kernel(const vec4_t<T>* __restrict__ asum, uint32_t n, T c, int fuse, LeapArgs<T> leap) {
+  const uint32_t b = blockIdx.x * 256 + threadIdx.x;
+  if (b >= n) return;
+  const vec4_t<T> s    = asum[b];
+  const vec4_t<T> anew = make_v4<T>(mul_rn(s.x, c), mul_rn(s.y, c), D == 3 ? mul_rn(s.z, c) : T(0), T(0));
+  leap.a[b] = anew;
+  if (fuse) leapfrog_body<T, D>(leap, b, anew);
+}
+
+struct SymState {
+  uint32_t B = 0, K = 0;
+  uint64_t slab = 0;
+  void* P    = nullptr;
+  void* asum = nullptr;
+};
+
+}  // namespace
+
+uint32_t all_pairs_sym_block(uint32_t n) {  // B = 1024 * ceil(n / 2^18)  =>  K = ceil(n / B) <= 256
+  uint32_t mult = (n + (1u << 18) - 1) >> 18;
+  return 1024u * (mult ? mult : 1);
+}
+
+template <typename T, int D, int RI, int MINB>
+static int sym_launch(nbx_engine* e, bool fuse) {
+  SymState* s = static_cast<SymState*>(e->sym);
+  if (!s) {
+    s       = new SymState();
+    e->sym  = s;
+    s->B    = all_pairs_sym_block(e->n);
+    s->K    = (e->n + s->B - 1) / s->B;
+    s->slab = uint64_t(s->K) * s->B;
+    NBX_CUDA(cudaMalloc(&s->P, sizeof(vec4_t<T>) * s->slab * s->K));
+    NBX_CUDA(cudaMalloc(&s->asum, sizeof(vec4_t<T>) * e->n_pad));
+  }
+  auto kern = all_pairs_sym_kernel<T, D, RI, MINB>;
+  const size_t smem = size_t(SYM_STAGES) * SYM_JT * sizeof(vec4_t<T>) + size_t(SYM_WARPS) * SYM_JT * 3 * sizeof(T) + SYM_STAGES * sizeof(uint64_t);
+  static bool attr_done = false;
+  if (!attr_done) {
+    NBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  const uint32_t world = uint32_t(e->cfg.world_size), rank = uint32_t(e->cfg.rank);
+  const uint64_t units = uint64_t(s->K) * (s->K + 1) / 2;
+  const uint32_t mine  = uint32_t((units > rank ? units - rank + world - 1 : 0) / world);
+  SymArgs<T> p;
+  p.xm = static_cast<const vec4_t<T>*>(e->xm[e->cur]);
+  p.P  = static_cast<vec4_t<T>*>(s->P);
+  p.slab = s->slab;
+  p.B = s->B;
+  p.K = s->K;
+  p.unit_begin  = rank;
+  p.unit_stride = world;
+  if (mine) kern<<<mine, 256, smem, e->stream>>>(p);
+  e->launches++;
+  LeapArgs<T> leap;
+  leap.xm_in  = static_cast<const vec4_t<T>*>(e->xm[e->cur]);
+  leap.xm_out = static_cast<vec4_t<T>*>(e->xm[e->cur ^ 1]);
+  leap.v  = static_cast<vec4_t<T>*>(e->v);
+  leap.a  = static_cast<vec4_t<T>*>(e->a);
+  leap.ao = static_cast<vec4_t<T>*>(e->ao);
+  leap.dt = T(e->cfg.dt);
+  const unsigned gb = (e->n + 255) / 256;
+  if (world == 1) {
+    sym_reduce_kernel<T, D><<<gb, 256, 0, e->stream>>>(p.P, s->slab, s->B, s->K, e->n, 0, 1, T(e->cfg.G), 1, fuse ? 1 : 0,
+                                                      static_cast<vec4_t<T>*>(s->asum), leap);
+    e->launches++;
+  } else {
+    sym_reduce_kernel<T, D><<<gb, 256, 0, e->stream>>>(p.P, s->slab, s->B, s->K, e->n, rank, world, T(e->cfg.G), 0, 0,
+                                                      static_cast<vec4_t<T>*>(s->asum), leap);
+    NBX_TRY(comm_allreduce_sum(e, s->asum, size_t(e->n) * 4));
+    sym_finish_kernel<T, D><<<gb, 256, 0, e->stream>>>(static_cast<const vec4_t<T>*>(s->asum), e->n, T(e->cfg.G), fuse ? 1 : 0, leap);
+    e->launches += 2;
+  }
+  NBX_CUDA(cudaGetLastError());
+  return NBX_OK;
+}
+
+bool all_pairs_sym_enabled(const nbx_engine* e) {
+  if (e->algo != NBX_ALL_PAIRS || (e->cfg.flags & NBX_FLAG_ALLPAIRS_ORDERED)) return false;
+  if (e->cfg.flags & NBX_FLAG_ALLPAIRS_SYMMETRIC) return true;
+  return e->n >= 65536;  // below that there are too few (I, J) units to fill 148 SMs
+}
+
+int all_pairs_sym_force(nbx_engine* e, bool fuse) {
+  if (e->prec == 4) return e->dim == 2 ? sym_launch<float, 2, 4, 2>(e, fuse) : sym_launch<float, 3, 4, 2>(e, fuse);
+  return e->dim == 2 ? sym_launch<double, 2, 2, 2>(e, fuse) : sym_launch<double, 3, 2, 2>(e, fuse);
+}
+
+void all_pairs_sym_destroy(nbx_engine* e) {
+  SymState* s = static_cast<SymState*>(e->sym);
+  if (!s) return;
+  if (s->P) cudaFree(s->P);
+  if (s->asum) cudaFree(s->asum);
+  delete s;
+  e->sym = nullptr;
+}
+
+}  // namespace nbx

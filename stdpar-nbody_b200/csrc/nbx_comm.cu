@@ -15,7 +15,7 @@ namespace {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
-constexpr int ncclChar = 0;
+constexpr int ncclChar = 0, ncclFloat = 7, ncclDouble = 8, ncclSum = 0;
 
 struct NcclApi {
   void* lib = nullptr;
@@ -23,6 +23,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int)                                     = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t)                                                               = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t)                  = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t)             = nullptr;
   const char* (*GetErrorString)(ncclResult_t)                                                           = nullptr;
   bool ok = false;
 };
@@ -42,8 +43,9 @@ NcclApi& api() {
   a.CommInitRank   = (decltype(a.CommInitRank))dlsym(a.lib, "ncclCommInitRank");
   a.CommDestroy    = (decltype(a.CommDestroy))dlsym(a.lib, "ncclCommDestroy");
   a.AllGather      = (decltype(a.AllGather))dlsym(a.lib, "ncclAllGather");
+  a.AllReduce      = (decltype(a.AllReduce))dlsym(a.lib, "ncclAllReduce");
   a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.lib, "ncclGetErrorString");
-  a.ok             = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.GetErrorString;
+  a.ok             = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.AllReduce && a.GetErrorString;
   return a;
 }
 
@@ -86,6 +88,16 @@ int comm_allgather(nbx_engine* e, void* vec4_array) {
   const size_t bytes = rec_bytes(e) * e->chunk;
   ncclResult_t r = api().AllGather(base + bytes * e->cfg.rank, base, bytes, ncclChar, (ncclComm_t)e->comm, e->stream);
   if (r != 0) return nccl_fail("ncclAllGather", r);
+  return NBX_OK;
+}
+
+// sum over ranks, in place (symmetric all-pairs: per-rank partial accelerations -> total)
+int comm_allreduce_sum(nbx_engine* e, void* buffer, size_t count) {
+  if (e->cfg.world_size <= 1) return NBX_OK;
+  if (!e->comm) return fail(NBX_ERR_COMM, "multi-GPU engine used before nbx_comm_init_rank");
+  PhaseTimer pt(e, PH_COMM);
+  ncclResult_t r = api().AllReduce(buffer, buffer, count, e->prec == 4 ? ncclFloat : ncclDouble, ncclSum, (ncclComm_t)e->comm, e->stream);
+  if (r != 0) return nccl_fail("ncclAllReduce", r);
   return NBX_OK;
 }
 

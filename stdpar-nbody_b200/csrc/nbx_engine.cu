@@ -162,7 +162,7 @@ static int one_step(nbx_engine* e) {
       return NBX_OK;
     default: return fail(NBX_ERR_INVALID, "unknown algorithm");
   }
-  if (multi) NBX_TRY(comm_allgather_positions(e));
+  if (multi && !all_pairs_sym_enabled(e)) NBX_TRY(comm_allgather_positions(e));
   return NBX_OK;
 }
 
@@ -239,7 +239,11 @@ int nbx_create(const nbx_config* cfg, nbx_engine** out) {
   const size_t rb = rec_bytes(e);
   // position buffers carry a zero-mass tail (n_pad - n records of padding + one all-pairs tile) so that tile
   // loads never need a bounds check: a zero-mass source contributes exactly 0.
-  const size_t pos_records = size_t(e->n_pad) + 1024;
+  size_t pos_records = size_t(e->n_pad) + 1024;
+  if (e->algo == NBX_ALL_PAIRS) {  // the symmetric kernel reads whole blocks of B bodies
+    const size_t B = all_pairs_sym_block(e->n);
+    pos_records    = std::max(pos_records, (size_t(e->n) + B - 1) / B * B + 1024);
+  }
   for (int k = 0; k < 2; ++k) {
     NBX_CUDA_B(cudaMalloc(&e->xm[k], rb * pos_records));
     NBX_CUDA_B(cudaMemsetAsync(e->xm[k], 0, rb * pos_records, e->stream));
@@ -267,6 +271,7 @@ int nbx_destroy(nbx_engine* e) {
   bvh_destroy(e);
   octree_destroy(e);
   sorter_destroy(e);
+  all_pairs_sym_destroy(e);
   void* bufs[] = {e->xm[0], e->xm[1], e->v, e->a, e->ao, e->v_alt, e->a_alt, e->ao_alt, e->partial, e->tickets, e->stage};
   for (void* b : bufs)
     if (b) cudaFree(b);

@@ -92,6 +92,7 @@ struct nbx_engine {
   void* bvh = nullptr;
   void* octree = nullptr;
   void* sorter = nullptr;
+  void* sym = nullptr;  // symmetric all-pairs state (nbx_allpairs_sym.cu)
 
   // NCCL (multi-GPU)
   void* comm = nullptr;
@@ -131,6 +132,11 @@ int accelerate_step(nbx_engine* e);                               // over this r
 int accelerate_range(nbx_engine* e, uint32_t begin, uint32_t end);  // over [begin, end)
 int calc_energies(nbx_engine* e, double* kinetic, double* grav);
 int measure_fma_peak(int device, int precision, double* tflops);
+// nbx_allpairs_sym.cu : Newton's-third-law variant of all_pairs_force
+bool all_pairs_sym_enabled(const nbx_engine* e);
+uint32_t all_pairs_sym_block(uint32_t n);
+int all_pairs_sym_force(nbx_engine* e, bool fuse_integrate);
+void all_pairs_sym_destroy(nbx_engine* e);
 // nbx_sort.cu : stable LSD radix sort of (u64 key, u32 value) pairs
 int sorter_create(nbx_engine* e, uint32_t n);
 void sorter_destroy(nbx_engine* e);
@@ -166,6 +172,7 @@ int comm_unique_id(void* id128);
 int comm_init_rank(nbx_engine* e, const void* id128);
 int comm_allgather_positions(nbx_engine* e);  // all-gather xm[cur] shards (chunk records per rank), in place
 int comm_allgather(nbx_engine* e, void* vec4_array);
+int comm_allreduce_sum(nbx_engine* e, void* buffer, size_t count);  // in place, `count` elements of the engine's precision
 void comm_destroy(nbx_engine* e);
 
 }  // namespace nbx

@@ -20,6 +20,8 @@ ALGORITHMS = {"all-pairs": ALL_PAIRS, "all-pairs-collapsed": ALL_PAIRS_COLLAPSED
 F32, F64 = 4, 8
 FLAG_COLLAPSED_FIX_Z = 0x1
 FLAG_NO_FUSED_INTEGRATE = 0x2
+FLAG_ALLPAIRS_ORDERED = 0x4
+FLAG_ALLPAIRS_SYMMETRIC = 0x8
 UNIQUE_ID_BYTES = 128
 PHASES = ("force", "accel", "bbox", "sort", "build", "multipoles", "traverse", "comm")
 

@@ -168,3 +168,53 @@ def test_full_size_properties_1M(oracle_fast):
     assert rms(err) <= 2 * rms(rel_err(ref32, truth)) + 1e-7
     f = out["a"].astype(np.float64) * s["m"].astype(np.float64)[:, None]
     assert np.abs(f.sum(0)).max() <= 1e-4 * np.abs(f).sum(0).max()
+
+
+# ---- symmetric (Newton's third law) all-pairs: default for n >= 65536, forced here at small n ---------------------------------
+@pytest.mark.parametrize("tag,dim", CASES, ids=IDS)
+@pytest.mark.parametrize("n", [2, 1001, 4096, 5000])
+def test_symmetric_force_vs_oracle(oracle, oracle_fast, tag, dim, n):
+    dt = DT[tag]
+    s = oracle.galaxy(n, dt, dim)
+    sym = run_force(s, flags=nbx.FLAG_ALLPAIRS_SYMMETRIC)
+    ordered = run_force(s, flags=nbx.FLAG_ALLPAIRS_ORDERED)
+    truth = oracle_fast.all_pairs_force_truth(s["m"], s["x"], s["G"])
+    err = rel_err(sym["a"], truth)
+    tol_rms, tol_max = TOL_A[np.dtype(dt)]
+    assert rms(err) <= tol_rms and err.max() <= tol_max, (rms(err), err.max())
+    # same pair terms, different summation order only
+    assert rel_err(sym["a"], ordered["a"]).max() <= (2e-4 if dt == np.float32 else 1e-12)
+    assert np.isfinite(sym["a"]).all()
+
+
+@pytest.mark.parametrize("tag,dim", CASES, ids=IDS)
+def test_symmetric_steps_fused_equals_unfused_and_reproducible(oracle, tag, dim):
+    dt = DT[tag]
+    s = oracle.galaxy(3000, dt, dim)
+    outs = []
+    for flags in (nbx.FLAG_ALLPAIRS_SYMMETRIC, nbx.FLAG_ALLPAIRS_SYMMETRIC | nbx.FLAG_NO_FUSED_INTEGRATE,
+                  nbx.FLAG_ALLPAIRS_SYMMETRIC):
+        with nbx.Engine(3000, dim, dt, "all-pairs", s["dt"], s["G"], flags=flags) as e:
+            e.upload_state(s)
+            e.step(STEPS)
+            outs.append(e.download())
+    for k in ("x", "v", "a", "ao"):
+        assert same(outs[0][k], outs[1][k]), k   # fused epilogue == separate kernels
+        assert same(outs[0][k], outs[2][k]), k   # no atomics: bit-reproducible run to run
+    ref = oracle.run("all-pairs", s, STEPS)
+    tol = 1e-5 if tag == "f32" else 1e-11
+    assert rms(rel_err(outs[0]["x"], ref["x"])) <= tol
+
+
+@pytest.mark.parametrize("flags", [0, 0x4], ids=["symmetric-default", "ordered"])
+def test_both_kernels_at_131072(oracle_fast, flags):
+    n = 131072
+    s = oracle_fast.galaxy(n, np.float32, 3)
+    out = run_force(s, flags=flags)
+    rng = np.random.default_rng(2)
+    targets = np.sort(rng.choice(n, 64, replace=False)).astype(np.uint32)
+    truth = oracle_fast.all_pairs_force_truth(s["m"], s["x"], s["G"], targets=targets)
+    err = rel_err(out["a"][targets], truth)
+    assert rms(err) <= 5e-5 and err.max() <= 5e-4, (rms(err), err.max())
+    f = out["a"].astype(np.float64) * s["m"].astype(np.float64)[:, None]
+    assert np.abs(f.sum(0)).max() <= 1e-4 * np.abs(f).sum(0).max()

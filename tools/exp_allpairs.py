@@ -21,7 +21,8 @@ s = orc.galaxy(n, dt, dim)
 rng = np.random.default_rng(0)
 targets = np.sort(rng.choice(n, 256, replace=False)).astype(np.uint32)
 truth = orc.all_pairs_force_truth(s["m"], s["x"], s["G"], targets=targets)
-with nbx.Engine(n, dim, dt, "all-pairs", s["dt"], s["G"]) as e:
+flags = int(os.environ.get("EXP_FLAGS", "0"))
+with nbx.Engine(n, dim, dt, "all-pairs", s["dt"], s["G"], flags=flags) as e:
     e.upload_state(s)
     e.all_pairs_force()
     a = e.download(("a",))["a"]
