@@ -318,6 +318,12 @@ def main_nbx(args):
                "h2d_bytes_per_step": int(n * (1 + 4 * dim) * isz), "d2h_bytes_per_step": int(n * dim * isz),
                "ms_per_step": 1e3 * e2e_s / args.steps}
 
+    if args.algorithm == "all-pairs" and n >= 65536:
+        parallelism = f"block-pair units dealt round-robin x{world}, NCCL all-reduce of accelerations"
+    elif args.algorithm.startswith("all-pairs"):
+        parallelism = f"targets sharded x{world}, NCCL all-gather of positions"
+    else:
+        parallelism = f"replicated tree build, traversal sharded x{world}, NCCL all-gather of accelerations"
     line = None
     if rank == 0:
         clk = clocks.summary()
@@ -325,13 +331,14 @@ def main_nbx(args):
         if args.algorithm.startswith("all-pairs"):
             prec = nbx.F32 if dt == np.float32 else nbx.F64
             peak = nbx.measure_fma_peak(prec, local_rank)
-            ts, te = nbx.shard_bounds(n, rank, world)
-            flops = (te - ts) * (n - 1) * FLOP_PER_PAIR[dim]
+            flops = n * (n - 1) * FLOP_PER_PAIR[dim] / world
             achieved = flops / (ph["force"] * 1e-3) / 1e12 if ph.get("force") else None
             roofline = {"bound": "fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                         "frac": achieved / peak if achieved and peak else None, "traffic": None,
-                        "kernel": "all_pairs_kernel", "kernel_ms": ph.get("force"),
-                        "note": f"{FLOP_PER_PAIR[dim]:.0f} algorithmic flop/pair x pairs of this rank / force-kernel time; peak = "
+                        "kernel": "all_pairs_sym_kernel" if (n >= 65536 and args.algorithm == "all-pairs") else "all_pairs_kernel", "kernel_ms": ph.get("force"),
+                        "note": f"{FLOP_PER_PAIR[dim]:.0f} algorithmic flop per ORDERED pair x n(n-1)/ranks / force time "
+                                "(pair kernel + partial-sum reduction); for n >= 65536 the kernel evaluates each unordered "
+                                "pair once (Newton's third law, src/all_pairs.h:41-42 TODO) and applies it to both bodies; peak = "
                                 f"{'FFMA' if prec == nbx.F32 else 'DFMA'} microbenchmark measured in this run "
                                 "(MEASURED_PEAKS.json has no FP32/FP64 FMA figure)"}
         else:
@@ -360,7 +367,7 @@ def main_nbx(args):
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32" if dt == np.float32 else "f64",
                 "data": "synthetic (reference galaxy model, mt19937{42}, generated on the host)",
-                "config": {"workload": workload_name(args, n), "parallelism": f"targets sharded x{world}, NCCL all-gather of positions",
+                "config": {"workload": workload_name(args, n), "parallelism": parallelism,
                            "l2": "512 MiB flush write between timed steps", "phase_ms": ph},
                 "clocks": clk, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline}
         if not args.no_cpu_baseline and world == 1:

@@ -183,7 +183,7 @@ def test_symmetric_force_vs_oracle(oracle, oracle_fast, tag, dim, n):
     tol_rms, tol_max = TOL_A[np.dtype(dt)]
     assert rms(err) <= tol_rms and err.max() <= tol_max, (rms(err), err.max())
     # same pair terms, different summation order only
-    assert rel_err(sym["a"], ordered["a"]).max() <= (2e-4 if dt == np.float32 else 1e-12)
+    assert rel_err(sym["a"], ordered["a"]).max() <= (1e-3 if dt == np.float32 else 1e-12)
     assert np.isfinite(sym["a"]).all()
 
 
