@@ -372,6 +372,12 @@ def main_nbx(args):
                 "clocks": clk, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args)
+            try:  # context only: the oracle port (-Ofast, OpenMP) on ALL host cores, same bounded sample
+                rate, cores = cpu_port_rate(args, sample_n(args), 1)
+                line["cpu_port_all_cores"] = {"value": rate, "unit": unit, "cores": cores, "kind": "port",
+                                              "sample": f"oracle port (-Ofast, OpenMP) {workload_name(args, sample_n(args))}, 1 step"}
+            except Exception as ex:  # noqa: BLE001 - the extra figure must never break the bench line
+                line["cpu_port_all_cores"] = {"error": str(ex)}
         print(json.dumps(line), flush=True)
     eng.close()
     if dist:

@@ -373,11 +373,13 @@ __global__ void __launch_bounds__(128) bvh_force_warp_kernel(const vec4_t<T>* __
         if (bidx < n) {
           const vec4_t<T> b = xm[bidx];
           if (act && bidx != i) {
-            T d2 = dist2_exact<T, D>(xs.x, xs.y, xs.z, b.x, b.y, b.z);
-            T s  = b.w * inv_dist3(d2);
-            ax = fma(b.x - xs.x, s, ax);
-            ay = fma(b.y - xs.y, s, ay);
-            if (D == 3) az = fma(b.z - xs.z, s, az);
+            const T dx = sub_rn(b.x, xs.x), dy = sub_rn(b.y, xs.y), dz = D == 3 ? sub_rn(b.z, xs.z) : T(0);
+            T d2 = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
+            if (D == 3) d2 = add_rn(d2, mul_rn(dz, dz));
+            T s = b.w * inv_dist3(d2);
+            ax = fma(dx, s, ax);
+            ay = fma(dy, s, ay);
+            if (D == 3) az = fma(dz, s, az);
           }
         }
       }
@@ -391,12 +393,15 @@ __global__ void __launch_bounds__(128) bvh_force_warp_kernel(const vec4_t<T>* __
       const vec4_t<T> nm = node_m[k];
       const T w          = bw[k];
       if (act) {
-        const T d2 = dist2_exact<T, D>(xs.x, xs.y, xs.z, nm.x, nm.y, nm.z);
+        // (xj - xs) == -(xs - xj) exactly, so one difference serves the reference-order dist2 and the accumulation
+        const T dx = sub_rn(nm.x, xs.x), dy = sub_rn(nm.y, xs.y), dz = D == 3 ? sub_rn(nm.z, xs.z) : T(0);
+        T d2 = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
+        if (D == 3) d2 = add_rn(d2, mul_rn(dz, dz));
         if (mul_rn(w, w) < mul_rn(theta2, d2)) {
           T s = nm.w * inv_dist3(d2);
-          ax = fma(nm.x - xs.x, s, ax);
-          ay = fma(nm.y - xs.y, s, ay);
-          if (D == 3) az = fma(nm.z - xs.z, s, az);
+          ax = fma(dx, s, ax);
+          ay = fma(dy, s, ay);
+          if (D == 3) az = fma(dz, s, az);
           covered += 1u << (levels - cl);
           if (COUNT) n_take += 1;
           if (!(k & 1)) level -= 1;  // right child (or root): continue one level up; left child: sibling, same level
