@@ -131,3 +131,22 @@ def test_csv_and_saved_positions(tmp_path):
     ea, eb = open(d1 / "energy.bin", "rb").read(), open(d2 / "energy.bin", "rb").read()
     assert len(ea) == len(eb) and ea[:8] == eb[:8]
     assert np.allclose(np.frombuffer(ea, np.float64, offset=8), np.frombuffer(eb, np.float64, offset=8), rtol=1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not O.ref_available(3), reason="oracle/_ref not built")
+def test_load_workload_matches_reference_binary(tmp_path):
+    """--workload load <file.bin> (src/saving.h:25-68; writer: scripts/thuering_nbody/conv_csv.py:62-80)."""
+    rng = np.random.default_rng(4)
+    n, dim = 50, 3
+    body = np.concatenate([rng.random((n, 1)) * 5, rng.standard_normal((n, dim)) * 10, rng.standard_normal((n, dim)) * 0.01], axis=1)
+    f = tmp_path / "in.bin"
+    with open(f, "wb") as fh:
+        fh.write(np.array([n, dim], np.uint32).tobytes())
+        fh.write(np.array([0.5, 1e-3], np.float32).tobytes())
+        fh.write(body.astype(np.float32).tobytes())
+    args = ["-s", "12", "--workload", "load", str(f), "--algorithm", "all-pairs", "--precision", "double", "--print-state"]
+    mine = run(3, args).stdout
+    ref = subprocess.run([os.path.join(O.REF_DIR, "nbody_d3")] + args, capture_output=True, text=True).stdout
+    strip = lambda out: [ln for ln in out.splitlines() if not ln.startswith("Total time")]  # noqa: E731
+    assert strip(mine) == strip(ref)
