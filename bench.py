@@ -64,7 +64,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def __exit__(self, *a):
         if self.proc:
@@ -74,9 +74,14 @@ class ClockSampler:
             except subprocess.TimeoutExpired:
                 self.proc.kill()
 
-    def summary(self):
+    def summary(self, t0=None, t1=None):
+        """Median SM clock and active throttle reasons of the samples taken in [t0, t1] (the timed region); the sampler is
+        started before the warm-up so that it is already streaming when the region begins."""
+        rows = [r for ts, r in self.rows if (t0 is None or ts >= t0) and (t1 is None or ts <= t1 + 0.15)]
+        if not rows:
+            rows = [r for _, r in self.rows]
         sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx = max(mx, float(r[1]))
@@ -257,17 +262,19 @@ def main_nbx(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput -------------------------------------------------------------------------------
-    for _ in range(args.warmup):
-        eng.step(1)
-    eng.sync()
-    c0 = eng.counters()
-    step_ms = []
     with ClockSampler(local_rank) as clocks:
+        for _ in range(args.warmup):
+            eng.step(1)
+        eng.sync()
+        c0 = eng.counters()
+        step_ms = []
+        t_region0 = time.time()
         for _ in range(args.steps):
             flush_l2()
             barrier()
             step_ms.append(eng.step_timed(1))  # CUDA events on the engine stream around the whole step
         barrier()
+        t_region1 = time.time()
     c1 = eng.counters()
     total_ms = max_over_ranks(sum(step_ms))
     value = units_per_step(args, n) * args.steps / (total_ms * 1e-3)
@@ -326,7 +333,7 @@ def main_nbx(args):
         parallelism = f"replicated tree build, traversal sharded x{world}, NCCL all-gather of accelerations"
     line = None
     if rank == 0:
-        clk = clocks.summary()
+        clk = clocks.summary(t_region0, t_region1)
         roofline = None
         if args.algorithm.startswith("all-pairs"):
             prec = nbx.F32 if dt == np.float32 else nbx.F64
