@@ -72,6 +72,9 @@ struct OctreeState {
   uint2* meta        = nullptr;  // [cap] {next, depth | leaf<<8}
   uint32_t* rec_body = nullptr;  // [cap] first sorted body of the node (for the canonical path code)
   uint32_t* cell_pos = nullptr;  // [n] record index of internal cell c
+  uint32_t* cells_by_depth = nullptr;  // [n] record indices of the cells grouped by depth (for the level-wise up-pass)
+  uint32_t* depth_count = nullptr;     // [130] cells per depth -> exclusive offsets [0..128], cursor copy at +...
+  uint32_t* depth_cursor = nullptr;    // [129]
   vec4_t<T>* a_sorted = nullptr; // [n_pad] accelerations in sorted-slot order
   bool built = false;
 };
@@ -303,7 +306,7 @@ __global__ void __launch_bounds__(256) emit_records_kernel(const uint64_t* __res
                                                            const vec4_t<T>* __restrict__ xm, uint32_t n,
                                                            const uint32_t* __restrict__ delta, const uint32_t* __restrict__ cell_base,
                                                            uint32_t cap, vec4_t<T>* mono, uint2* meta, uint32_t* rec_body,
-                                                           uint32_t* cell_pos, Root<T>* root) {
+                                                           uint32_t* cell_pos, Root<T>* root, uint32_t* depth_count) {
   uint32_t s = blockIdx.x * 256 + threadIdx.x;
   if (s >= n) return;
   const uint32_t dn = delta[s];                      // delta_s + 1
@@ -338,20 +341,42 @@ __global__ void __launch_bounds__(256) emit_records_kernel(const uint64_t* __res
       meta[pos]     = make_uint2((e + 1) + cell_base[e + 1], depth);
       rec_body[pos] = s;
       cell_pos[cid] = pos;
+      atomicAdd(&depth_count[depth], 1u);
     }
   }
 }
 
 // ---- K8 monopoles: one launch per depth, deepest first (octree.h:205-216: m = sum m_c ; x = sum m_c*x_c / m) -------------
-template <typename T, int D>
-__global__ void __launch_bounds__(256) monopole_level_kernel(const uint32_t* __restrict__ cell_pos, const Root<T>* __restrict__ root,
-                                                             uint32_t depth, uint32_t cap, vec4_t<T>* mono, const uint2* __restrict__ meta) {
+// cells are first grouped by depth (counting sort: depth_count -> offsets -> cells_by_depth) so that every level launch only
+// touches its own cells.
+__global__ void depth_offsets_kernel(uint32_t* depth_count, uint32_t* depth_cursor) {
+  if (threadIdx.x != 0) return;
+  uint32_t run = 0;
+  for (int d = 0; d < 129; ++d) {
+    uint32_t c      = d < 128 ? depth_count[d] : 0;
+    depth_count[d]  = run;  // exclusive offsets
+    depth_cursor[d] = run;
+    run += c;
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) group_cells_kernel(const uint32_t* __restrict__ cell_pos, const Root<T>* __restrict__ root,
+                                                          const uint2* __restrict__ meta, uint32_t cap, uint32_t* depth_cursor,
+                                                          uint32_t* __restrict__ cells_by_depth) {
   uint32_t c = blockIdx.x * 256 + threadIdx.x;
   if (c >= root->cells) return;
   const uint32_t p = cell_pos[c];
   if (p >= cap) return;
-  const uint2 me = meta[p];
-  if ((me.y & 0xff) != depth) return;
+  cells_by_depth[atomicAdd(&depth_cursor[meta[p].y & 0xff], 1u)] = p;
+}
+template <typename T, int D>
+__global__ void __launch_bounds__(256) monopole_level_kernel(const uint32_t* __restrict__ cells_by_depth, const uint32_t* __restrict__ depth_off,
+                                                             uint32_t depth, uint32_t cap, vec4_t<T>* mono, const uint2* __restrict__ meta) {
+  const uint32_t first = depth_off[depth], count = depth_off[depth + 1] - first;
+  uint32_t c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= count) return;
+  const uint32_t p = cells_by_depth[first + c];
+  const uint2 me   = meta[p];
   T m = 0, x = 0, y = 0, z = 0;
   uint32_t q = p + 1;
   while (q < me.x && q < cap) {  // children in child order
@@ -480,6 +505,9 @@ static int create_impl(nbx_engine* e) {
   NBX_CUDA(cudaMalloc(&s->meta, sizeof(uint2) * s->cap));
   NBX_CUDA(cudaMalloc(&s->rec_body, sizeof(uint32_t) * s->cap));
   NBX_CUDA(cudaMalloc(&s->cell_pos, sizeof(uint32_t) * n));
+  NBX_CUDA(cudaMalloc(&s->cells_by_depth, sizeof(uint32_t) * n));
+  NBX_CUDA(cudaMalloc(&s->depth_count, sizeof(uint32_t) * 130));
+  NBX_CUDA(cudaMalloc(&s->depth_cursor, sizeof(uint32_t) * 130));
   NBX_CUDA(cudaMalloc(&s->a_sorted, sizeof(vec4_t<T>) * e->n_pad));
   NBX_CUDA(cudaMemsetAsync(s->a_sorted, 0, sizeof(vec4_t<T>) * e->n_pad, e->stream));
   NBX_TRY(sorter_create(e, e->n));
@@ -491,7 +519,7 @@ static void destroy_impl(nbx_engine* e) {
   auto* s = st<T>(e);
   if (!s) return;
   void* bufs[] = {s->root, s->partial, s->keys, s->skeys, s->keys_lo, s->skeys_lo, s->keys_tmp, s->perm_tmp, s->perm, s->delta, s->cnt, s->blocksum,
-                  s->mono, s->meta, s->rec_body, s->cell_pos, s->a_sorted};
+                  s->mono, s->meta, s->rec_body, s->cell_pos, s->cells_by_depth, s->depth_count, s->depth_cursor, s->a_sorted};
   for (void* b : bufs)
     if (b) cudaFree(b);
   delete s;
@@ -541,14 +569,18 @@ static int build_impl(nbx_engine* e) {
     scan_reduce_kernel<<<nb, 1024, 0, e->stream>>>(s->cnt, count, s->blocksum);
     scan_blocksums_kernel<<<1, 1024, 0, e->stream>>>(s->blocksum, nb, nullptr);
     scan_apply_kernel<<<nb, 1024, 0, e->stream>>>(s->cnt, count, s->blocksum);
+    NBX_CUDA(cudaMemsetAsync(s->depth_count, 0, sizeof(uint32_t) * 130, e->stream));
     emit_records_kernel<T, D><<<gb, 256, 0, e->stream>>>(s->skeys, s->deep ? s->skeys_lo : nullptr, s->perm, xm, n, s->delta, s->cnt,
-                                                        s->cap, s->mono, s->meta, s->rec_body, s->cell_pos, s->root);
+                                                        s->cap, s->mono, s->meta, s->rec_body, s->cell_pos, s->root, s->depth_count);
     e->launches += 4;
   }
   {
     PhaseTimer pt(e, PH_MONO);
+    depth_offsets_kernel<<<1, 32, 0, e->stream>>>(s->depth_count, s->depth_cursor);
+    group_cells_kernel<T><<<gb, 256, 0, e->stream>>>(s->cell_pos, s->root, s->meta, s->cap, s->depth_cursor, s->cells_by_depth);
+    e->launches += 2;
     for (int depth = (s->deep ? 2 : 1) * KeyTraits<D>::MAXL - 1; depth >= 0; --depth) {
-      monopole_level_kernel<T, D><<<gb, 256, 0, e->stream>>>(s->cell_pos, s->root, uint32_t(depth), s->cap, s->mono, s->meta);
+      monopole_level_kernel<T, D><<<gb, 256, 0, e->stream>>>(s->cells_by_depth, s->depth_count, uint32_t(depth), s->cap, s->mono, s->meta);
       e->launches++;
     }
   }

@@ -3,7 +3,8 @@
 // Replaces the reference's std::sort(par_unseq, pair<key,idx>) (src/bvh.h:62-69). 8 bits per pass; each pass is
 //   digit_histogram  : per-tile digit counts            -> hist[digit][tile]
 //   row_scan         : exclusive scan of every digit row (+ digit totals)
-//   scatter          : warp-match ranking (stable) + global offsets -> write (key, index) to its sorted place
+//   scatter          : warp-match ranking (stable) + global offsets; the tile is first staged in shared memory in sorted
+//                      order so that the write-out is coalesced per digit run
 // A tile is RS_THREADS x RS_ITEMS consecutive elements laid out warp-striped, so loads are fully coalesced and the
 // element order inside a tile is (warp, iteration, lane) — ranks are assigned in exactly that order => STABLE, so ties
 // keep their current index order (the reference's unstable std::sort leaves ties undefined).
@@ -83,15 +84,23 @@ __global__ void __launch_bounds__(1024) row_scan_kernel(uint32_t* hist, uint32_t
   if (threadIdx.x == 0) totals[blockIdx.x] = carry;
 }
 
+// dynamic shared memory of scatter_kernel: per-warp digit counters + the tile staged in sorted order
+constexpr size_t RS_SMEM = sizeof(uint32_t) * RS_WARPS * RS_RADIX + sizeof(uint64_t) * RS_TILE + sizeof(uint32_t) * RS_TILE;
+
 __global__ void __launch_bounds__(RS_THREADS) scatter_kernel(const uint64_t* __restrict__ keys_in,
                                                              const uint32_t* __restrict__ vals_in,  // NULL => iota
                                                              uint64_t* __restrict__ keys_out,
                                                              uint32_t* __restrict__ vals_out, uint32_t n, int shift,
                                                              const uint32_t* __restrict__ hist, uint32_t ntiles,
                                                              const uint32_t* __restrict__ totals) {
-  __shared__ uint32_t warp_count[RS_WARPS][RS_RADIX];
-  __shared__ uint32_t offset[RS_RADIX];
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  uint32_t(*warp_count)[RS_RADIX] = reinterpret_cast<uint32_t(*)[RS_RADIX]>(rs_smem);
+  uint64_t* skey                  = reinterpret_cast<uint64_t*>(rs_smem + sizeof(uint32_t) * RS_WARPS * RS_RADIX);
+  uint32_t* sval                  = reinterpret_cast<uint32_t*>(skey + RS_TILE);
+  __shared__ uint32_t gbase[RS_RADIX];   // global position of this tile's first element of digit d
+  __shared__ uint32_t dstart[RS_RADIX];  // position of digit d inside the sorted tile
   __shared__ uint32_t scan_tmp[RS_RADIX / 32];
+  __shared__ uint32_t scan_tmp2[RS_RADIX / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int q = threadIdx.x; q < RS_WARPS * RS_RADIX; q += RS_THREADS) (&warp_count[0][0])[q] = 0;
 
@@ -111,19 +120,20 @@ __global__ void __launch_bounds__(RS_THREADS) scatter_kernel(const uint64_t* __r
   if (threadIdx.x < RS_RADIX) {
     uint32_t before = 0;
     for (int w = 0; w < warp; ++w) before += scan_tmp[w];
-    offset[threadIdx.x] = before + inc - tot + hist[size_t(threadIdx.x) * ntiles + blockIdx.x];
+    gbase[threadIdx.x] = before + inc - tot + hist[size_t(threadIdx.x) * ntiles + blockIdx.x];
   }
 
   uint64_t key[RS_ITEMS];
   uint32_t val[RS_ITEMS], rank[RS_ITEMS];
-  const uint32_t base = blockIdx.x * RS_TILE + warp * (32 * RS_ITEMS) + lane;
+  const uint32_t tile0 = blockIdx.x * RS_TILE;
+  const uint32_t base  = tile0 + warp * (32 * RS_ITEMS) + lane;
 #pragma unroll
   for (int k = 0; k < RS_ITEMS; ++k) {
     uint32_t idx = base + k * 32;
     key[k]       = idx < n ? keys_in[idx] : ~0ull;
     val[k]       = idx < n ? (vals_in ? vals_in[idx] : idx) : 0xffffffffu;
   }
-  __syncthreads();  // warp_count zeroed, offset ready
+  __syncthreads();  // warp_count zeroed, gbase ready
 #pragma unroll
   for (int k = 0; k < RS_ITEMS; ++k) {
     uint32_t d     = uint32_t(key[k] >> shift) & 0xff;
@@ -136,26 +146,50 @@ __global__ void __launch_bounds__(RS_THREADS) scatter_kernel(const uint64_t* __r
     rank[k] = cnt + __popc(lt);
   }
   __syncthreads();
-  // per digit: exclusive prefix over the warps of this CTA
+  // per digit: exclusive prefix over the warps of this CTA, then over the digits (position inside the sorted tile)
+  uint32_t dcount = 0, dinc = 0;
   if (threadIdx.x < RS_RADIX) {
     uint32_t run = 0;
 #pragma unroll
     for (int w = 0; w < RS_WARPS; ++w) {
-      uint32_t c                   = warp_count[w][threadIdx.x];
+      uint32_t c                 = warp_count[w][threadIdx.x];
       warp_count[w][threadIdx.x] = run;
       run += c;
     }
+    dcount = run;
+    dinc   = run;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, dinc, off);
+      if (lane >= off) dinc += t;
+    }
+    if (lane == 31) scan_tmp2[warp] = dinc;
   }
   __syncthreads();
+  if (threadIdx.x < RS_RADIX) {
+    uint32_t before = 0;
+    for (int w = 0; w < warp; ++w) before += scan_tmp2[w];
+    dstart[threadIdx.x] = before + dinc - dcount;
+  }
+  __syncthreads();
+  // stage the tile in sorted order (stable: (warp, iteration, lane) order inside every digit)
 #pragma unroll
   for (int k = 0; k < RS_ITEMS; ++k) {
-    uint32_t idx = base + k * 32;
-    if (idx < n) {
-      uint32_t d   = uint32_t(key[k] >> shift) & 0xff;
-      uint32_t pos = offset[d] + warp_count[warp][d] + rank[k];
-      keys_out[pos] = key[k];
-      vals_out[pos] = val[k];
-    }
+    uint32_t d  = uint32_t(key[k] >> shift) & 0xff;
+    uint32_t lp = dstart[d] + warp_count[warp][d] + rank[k];
+    skey[lp]    = key[k];
+    sval[lp]    = val[k];
+  }
+  __syncthreads();
+  // coalesced write-out: consecutive threads -> consecutive addresses inside every digit run. Elements past n carry the
+  // all-ones key, sort to the very end of the tile and are simply not written.
+  const uint32_t count = n - tile0 < uint32_t(RS_TILE) ? n - tile0 : uint32_t(RS_TILE);
+  for (uint32_t i = threadIdx.x; i < count; i += RS_THREADS) {
+    const uint64_t kk = skey[i];
+    const uint32_t d  = uint32_t(kk >> shift) & 0xff;
+    const uint32_t gp = gbase[d] + (i - dstart[d]);
+    keys_out[gp]      = kk;
+    vals_out[gp]      = sval[i];
   }
 }
 
@@ -173,6 +207,7 @@ int sorter_create(nbx_engine* e, uint32_t n) {
   }
   NBX_CUDA(cudaMalloc(&s->hist, sizeof(uint32_t) * size_t(RS_RADIX) * s->ntiles));
   NBX_CUDA(cudaMalloc(&s->totals, sizeof(uint32_t) * RS_RADIX));
+  NBX_CUDA(cudaFuncSetAttribute(scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM));
   return NBX_OK;
 }
 
@@ -206,7 +241,7 @@ int sort_pairs(nbx_engine* e, const uint64_t* keys_in, uint32_t n, int key_bits,
     uint32_t* vout  = last ? perm_out : s->vals[p & 1];
     digit_histogram_kernel<<<ntiles, RS_THREADS, 0, e->stream>>>(kin, n, 8 * p, s->hist, ntiles);
     row_scan_kernel<<<RS_RADIX, 1024, 0, e->stream>>>(s->hist, ntiles, s->totals);
-    scatter_kernel<<<ntiles, RS_THREADS, 0, e->stream>>>(kin, vin, kout, vout, n, 8 * p, s->hist, ntiles, s->totals);
+    scatter_kernel<<<ntiles, RS_THREADS, RS_SMEM, e->stream>>>(kin, vin, kout, vout, n, 8 * p, s->hist, ntiles, s->totals);
     e->launches += 3;
     kin = kout;
     vin = vout;

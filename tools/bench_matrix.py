@@ -16,6 +16,12 @@ CONFIGS = {
     "bvh10": ["--algorithm", "bvh", "-n", "10000000", "--dim", "3", "--precision", "float"],
     "bvh10d": ["--algorithm", "bvh", "-n", "10000000", "--dim", "3", "--precision", "double"],
     "c5": ["--algorithm", "bvh", "-n", "100000000", "--dim", "3", "--precision", "float"],
+    "s_ap": ["--algorithm", "all-pairs", "-n", "100000", "--dim", "3", "--precision", "double"],
+    "s_apc": ["--algorithm", "all-pairs-collapsed", "-n", "100000", "--dim", "3", "--precision", "double"],
+    "s_oct": ["--algorithm", "octree", "-n", "100000", "--dim", "3", "--precision", "double"],
+    "s_bvh": ["--algorithm", "bvh", "-n", "100000", "--dim", "3", "--precision", "double"],
+    "s_oct1m": ["--algorithm", "octree", "-n", "1000000", "--dim", "3", "--precision", "double"],
+    "s_bvh1m": ["--algorithm", "bvh", "-n", "1000000", "--dim", "3", "--precision", "double"],
     "oct1": ["--algorithm", "octree", "-n", "1000000", "--dim", "3", "--precision", "float"],
     "bvh1": ["--algorithm", "bvh", "-n", "1000000", "--dim", "3", "--precision", "float"],
 }
