@@ -297,6 +297,13 @@ __global__ void __launch_bounds__(1024) scan_apply_kernel(uint32_t* data, uint32
   }
 }
 
+template <typename T, int D>
+__device__ __forceinline__ void emit_records_body(const uint64_t* __restrict__ skeys, const uint64_t* __restrict__ skeys_lo,
+                                                  const uint32_t* __restrict__ perm, const vec4_t<T>* __restrict__ xm, uint32_t n,
+                                                  const uint32_t* __restrict__ delta, const uint32_t* __restrict__ cell_base,
+                                                  uint32_t cap, vec4_t<T>* mono, uint2* meta, uint32_t* rec_body,
+                                                  uint32_t* cell_pos, Root<T>* root, uint32_t* dhist);
+
 // One thread per sorted body s: emits its leaf record and the records of every cell that starts at s.
 // Record index of cell (s, depth d) = s + cell_id, cell_id = cell_base[s] + (d - first depth); of leaf s = s + cell_base[s+1].
 // `next` of a cell = record index right after its last body e: (e + 1) + cell_base[e + 1].
@@ -307,6 +314,21 @@ __global__ void __launch_bounds__(256) emit_records_kernel(const uint64_t* __res
                                                            const uint32_t* __restrict__ delta, const uint32_t* __restrict__ cell_base,
                                                            uint32_t cap, vec4_t<T>* mono, uint2* meta, uint32_t* rec_body,
                                                            uint32_t* cell_pos, Root<T>* root, uint32_t* depth_count) {
+  __shared__ uint32_t dhist[130];
+  for (int q = threadIdx.x; q < 130; q += 256) dhist[q] = 0;
+  __syncthreads();
+  emit_records_body<T, D>(skeys, skeys_lo, perm, xm, n, delta, cell_base, cap, mono, meta, rec_body, cell_pos, root, dhist);
+  __syncthreads();
+  for (int q = threadIdx.x; q < 130; q += 256)
+    if (dhist[q]) atomicAdd(&depth_count[q], dhist[q]);
+}
+
+template <typename T, int D>
+__device__ __forceinline__ void emit_records_body(const uint64_t* __restrict__ skeys, const uint64_t* __restrict__ skeys_lo,
+                                                  const uint32_t* __restrict__ perm, const vec4_t<T>* __restrict__ xm, uint32_t n,
+                                                  const uint32_t* __restrict__ delta, const uint32_t* __restrict__ cell_base,
+                                                  uint32_t cap, vec4_t<T>* mono, uint2* meta, uint32_t* rec_body,
+                                                  uint32_t* cell_pos, Root<T>* root, uint32_t* dhist) {
   uint32_t s = blockIdx.x * 256 + threadIdx.x;
   if (s >= n) return;
   const uint32_t dn = delta[s];                      // delta_s + 1
@@ -341,7 +363,7 @@ __global__ void __launch_bounds__(256) emit_records_kernel(const uint64_t* __res
       meta[pos]     = make_uint2((e + 1) + cell_base[e + 1], depth);
       rec_body[pos] = s;
       cell_pos[cid] = pos;
-      atomicAdd(&depth_count[depth], 1u);
+      atomicAdd(&dhist[depth], 1u);
     }
   }
 }
@@ -363,11 +385,25 @@ template <typename T>
 __global__ void __launch_bounds__(256) group_cells_kernel(const uint32_t* __restrict__ cell_pos, const Root<T>* __restrict__ root,
                                                           const uint2* __restrict__ meta, uint32_t cap, uint32_t* depth_cursor,
                                                           uint32_t* __restrict__ cells_by_depth) {
-  uint32_t c = blockIdx.x * 256 + threadIdx.x;
-  if (c >= root->cells) return;
-  const uint32_t p = cell_pos[c];
-  if (p >= cap) return;
-  cells_by_depth[atomicAdd(&depth_cursor[meta[p].y & 0xff], 1u)] = p;
+  __shared__ uint32_t cnt[130], base[130];
+  for (int q = threadIdx.x; q < 130; q += 256) cnt[q] = 0;
+  __syncthreads();
+  const uint32_t c = blockIdx.x * 256 + threadIdx.x;
+  uint32_t p = 0xffffffffu, d = 0, local = 0;
+  if (c < root->cells) {
+    p = cell_pos[c];
+    if (p < cap) {
+      d     = meta[p].y & 0xff;
+      local = atomicAdd(&cnt[d], 1u);  // order inside a depth does not matter: every cell is computed independently
+    } else {
+      p = 0xffffffffu;
+    }
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < 130; q += 256)
+    if (cnt[q]) base[q] = atomicAdd(&depth_cursor[q], cnt[q]);
+  __syncthreads();
+  if (p != 0xffffffffu) cells_by_depth[base[d] + local] = p;
 }
 template <typename T, int D>
 __global__ void __launch_bounds__(256) monopole_level_kernel(const uint32_t* __restrict__ cells_by_depth, const uint32_t* __restrict__ depth_off,
