@@ -357,11 +357,7 @@ template <typename T, int D, int TI, int BLOCK, int MINB>
 static int launch_all_pairs_cfg(nbx_engine* e, bool fuse, uint32_t nsplit, uint32_t tiles_per_split) {
   auto kern = all_pairs_kernel<T, D, TI, BLOCK, AP_TILE, AP_STAGES, MINB>;
   const size_t smem = size_t(AP_STAGES) * AP_TILE * sizeof(vec4_t<T>) + AP_STAGES * sizeof(uint64_t);
-  static bool attr_done = false;  // per template instantiation
-  if (!attr_done) {
-    NBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  NBX_TRY(ensure_dynamic_smem(e, kern, smem));
   const uint32_t nt      = e->te - e->tb;
   const uint32_t iblocks = (nt + BLOCK * TI - 1) / (BLOCK * TI);
   if (nsplit > 1) {

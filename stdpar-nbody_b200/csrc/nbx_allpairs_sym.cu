@@ -253,11 +253,7 @@ static int sym_launch(nbx_engine* e, bool fuse) {
   }
   auto kern = all_pairs_sym_kernel<T, D, RI, MINB>;
   const size_t smem = size_t(SYM_STAGES) * SYM_JT * sizeof(vec4_t<T>) + size_t(SYM_WARPS) * SYM_JT * 3 * sizeof(T) + SYM_STAGES * sizeof(uint64_t);
-  static bool attr_done = false;
-  if (!attr_done) {
-    NBX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  NBX_TRY(ensure_dynamic_smem(e, kern, smem));
   const uint32_t world = uint32_t(e->cfg.world_size), rank = uint32_t(e->cfg.rank);
   const uint64_t units = uint64_t(s->K) * (s->K + 1) / 2;
   const uint32_t mine  = uint32_t((units > rank ? units - rank + world - 1 : 0) / world);

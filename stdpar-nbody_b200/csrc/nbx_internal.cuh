@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <set>
 #include <string>
 
 #include "nbx.h"
@@ -97,6 +98,10 @@ struct nbx_engine {
   // NCCL (multi-GPU)
   void* comm = nullptr;
 
+  // kernels whose >48 KB dynamic shared memory opt-in has been set for THIS engine's device (the attribute is
+  // per device, and engines of several devices can live in one process)
+  std::set<const void*> smem_opt_in;
+
   // counters / timing
   uint64_t launches = 0, h2d = 0, d2h = 0;
   bool phase_timing = false;
@@ -123,6 +128,15 @@ struct PhaseTimer {
 };
 
 inline size_t rec_bytes(const nbx_engine* e) { return size_t(4) * e->prec; }
+
+template <typename K>
+inline int ensure_dynamic_smem(nbx_engine* e, K kernel, size_t bytes) {
+  const void* key = reinterpret_cast<const void*>(kernel);
+  if (e->smem_opt_in.count(key)) return NBX_OK;
+  NBX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  e->smem_opt_in.insert(key);
+  return NBX_OK;
+}
 
 // ---- implemented per translation unit -------------------------------------------------------------------------
 // nbx_allpairs.cu

@@ -207,7 +207,7 @@ int sorter_create(nbx_engine* e, uint32_t n) {
   }
   NBX_CUDA(cudaMalloc(&s->hist, sizeof(uint32_t) * size_t(RS_RADIX) * s->ntiles));
   NBX_CUDA(cudaMalloc(&s->totals, sizeof(uint32_t) * RS_RADIX));
-  NBX_CUDA(cudaFuncSetAttribute(scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM));
+  NBX_TRY(ensure_dynamic_smem(e, scatter_kernel, RS_SMEM));
   return NBX_OK;
 }
 

@@ -1,0 +1,83 @@
+"""C-ABI behaviour on a GPU: call-order errors, partial upload/download, re-upload, extreme theta, tiny n."""
+import numpy as np
+import pytest
+
+import _pkg
+from golden_util import rel_err, same
+
+pytestmark = pytest.mark.gpu
+nbx = _pkg.load().nbx
+
+
+def test_call_order_errors(oracle):
+    s = oracle.galaxy(100, np.float32, 3)
+    with nbx.Engine(100, 3, np.float32, "bvh", s["dt"], s["G"]) as e:
+        e.upload_state(s)
+        with pytest.raises(nbx.NbxError) as ei:
+            e.hilbert_sort()           # before bounding_box
+        assert ei.value.code == -6
+        with pytest.raises(nbx.NbxError):
+            e.bvh_compute_force()      # before build_tree
+        with pytest.raises(nbx.NbxError):
+            e.octree_build()           # wrong engine kind
+    with nbx.Engine(100, 3, np.float32, "octree", s["dt"], s["G"]) as e:
+        e.upload_state(s)
+        with pytest.raises(nbx.NbxError):
+            e.octree_compute_force()   # before build
+        with pytest.raises(nbx.NbxError):
+            e.traversal_stats()
+    with nbx.Engine(100, 3, np.float32, "all-pairs", s["dt"], s["G"]) as e:
+        with pytest.raises(nbx.NbxError):
+            e.traversal_stats()
+
+
+def test_partial_upload_download_and_reupload(oracle):
+    s = oracle.galaxy(500, np.float64, 2)
+    with nbx.Engine(500, 2, np.float64, "all-pairs", s["dt"], s["G"]) as e:
+        e.upload(m=s["m"], x=s["x"])                      # v, a, ao stay zero
+        out = e.download()
+        assert same(out["x"], s["x"]) and same(out["m"], s["m"]) and not out["v"].any()
+        e.upload(v=s["v"])                                # later, only the velocities
+        assert same(e.download(("v",))["v"], s["v"])
+        e.step(2)
+        first = e.download()
+        e.upload_state(s)                                 # same engine, fresh state: identical trajectory
+        e.step(2)
+        second = e.download()
+        for k in ("x", "v", "a", "ao"):
+            assert same(first[k], second[k]), k
+        c = e.counters()
+        assert c["kernel_launches"] > 0 and c["h2d_bytes"] > 0 and c["d2h_bytes"] > 0
+
+
+@pytest.mark.parametrize("algo", ["octree", "bvh"])
+def test_extreme_theta(oracle, algo):
+    """theta = 0 opens everything (== all-pairs); a huge theta accepts the root at once (one monopole per body)."""
+    s = oracle.galaxy(400, np.float64, 3)
+    with nbx.Engine(400, 3, np.float64, algo, s["dt"], s["G"], theta=1e6) as e:
+        e.upload_state(s)
+        e.step(1)
+        st = e.traversal_stats()
+        a_big = e.download(("a",))["a"]
+    ref = oracle.run(algo, s, 1, 1e6)
+    assert rel_err(a_big, ref["a"]).max() < 1e-11
+    # octree: the root is accepted immediately; bvh: every body stops at the root or very near it
+    assert st["node_visits"] <= 400 * (1 if algo == "octree" else 3)
+
+
+@pytest.mark.parametrize("algo", ["all-pairs", "all-pairs-collapsed", "octree", "bvh"])
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_tiny_systems(oracle, algo, n):
+    if algo == "bvh" and n < 2:
+        with pytest.raises(nbx.NbxError):
+            nbx.Engine(1, 3, np.float32, "bvh", 1.0, 1.0)
+        return
+    s = oracle.galaxy(4, np.float64, 3)
+    s = {k: (v[:n].copy() if isinstance(v, np.ndarray) else v) for k, v in s.items()}
+    with nbx.Engine(n, 3, np.float64, algo, s["dt"], s["G"]) as e:
+        e.upload_state(s)
+        e.step(2)
+        out = e.download()
+    ref = oracle.run(algo, s, 2)
+    assert np.isfinite(out["x"]).all()
+    assert np.allclose(out["x"], ref["x"], rtol=1e-12, atol=1e-12)
