@@ -67,7 +67,8 @@ struct OctreeState {
   uint32_t* delta    = nullptr;  // [n] common-prefix levels of sorted neighbours s, s+1 (MAXL+1.. see kernel)
   uint32_t* cnt      = nullptr;  // [n+1] cells starting at sorted body s -> exclusive scan in place (cell_base)
   uint32_t* blocksum = nullptr;
-  uint32_t cap       = 0;        // record capacity = 2n + 1
+  uint32_t ccap      = 0;        // internal-cell capacity = max(n, 256)  (reference: max(2^D n, 1000) nodes, system.h:29)
+  uint32_t cap       = 0;        // record capacity = n + ccap + 1
   vec4_t<T>* mono    = nullptr;  // [cap]
   uint2* meta        = nullptr;  // [cap] {next, depth | leaf<<8}
   uint32_t* rec_body = nullptr;  // [cap] first sorted body of the node (for the canonical path code)
@@ -301,7 +302,7 @@ template <typename T, int D>
 __device__ __forceinline__ void emit_records_body(const uint64_t* __restrict__ skeys, const uint64_t* __restrict__ skeys_lo,
                                                   const uint32_t* __restrict__ perm, const vec4_t<T>* __restrict__ xm, uint32_t n,
                                                   const uint32_t* __restrict__ delta, const uint32_t* __restrict__ cell_base,
-                                                  uint32_t cap, vec4_t<T>* mono, uint2* meta, uint32_t* rec_body,
+                                                  uint32_t cap, uint32_t ccap, vec4_t<T>* mono, uint2* meta, uint32_t* rec_body,
                                                   uint32_t* cell_pos, Root<T>* root, uint32_t* dhist);
 
 // One thread per sorted body s: emits its leaf record and the records of every cell that starts at s.
@@ -312,12 +313,12 @@ __global__ void __launch_bounds__(256) emit_records_kernel(const uint64_t* __res
                                                            const uint32_t* __restrict__ perm,
                                                            const vec4_t<T>* __restrict__ xm, uint32_t n,
                                                            const uint32_t* __restrict__ delta, const uint32_t* __restrict__ cell_base,
-                                                           uint32_t cap, vec4_t<T>* mono, uint2* meta, uint32_t* rec_body,
+                                                           uint32_t cap, uint32_t ccap, vec4_t<T>* mono, uint2* meta, uint32_t* rec_body,
                                                            uint32_t* cell_pos, Root<T>* root, uint32_t* depth_count) {
   __shared__ uint32_t dhist[130];
   for (int q = threadIdx.x; q < 130; q += 256) dhist[q] = 0;
   __syncthreads();
-  emit_records_body<T, D>(skeys, skeys_lo, perm, xm, n, delta, cell_base, cap, mono, meta, rec_body, cell_pos, root, dhist);
+  emit_records_body<T, D>(skeys, skeys_lo, perm, xm, n, delta, cell_base, cap, ccap, mono, meta, rec_body, cell_pos, root, dhist);
   __syncthreads();
   for (int q = threadIdx.x; q < 130; q += 256)
     if (dhist[q]) atomicAdd(&depth_count[q], dhist[q]);
@@ -327,7 +328,7 @@ template <typename T, int D>
 __device__ __forceinline__ void emit_records_body(const uint64_t* __restrict__ skeys, const uint64_t* __restrict__ skeys_lo,
                                                   const uint32_t* __restrict__ perm, const vec4_t<T>* __restrict__ xm, uint32_t n,
                                                   const uint32_t* __restrict__ delta, const uint32_t* __restrict__ cell_base,
-                                                  uint32_t cap, vec4_t<T>* mono, uint2* meta, uint32_t* rec_body,
+                                                  uint32_t cap, uint32_t ccap, vec4_t<T>* mono, uint2* meta, uint32_t* rec_body,
                                                   uint32_t* cell_pos, Root<T>* root, uint32_t* dhist) {
   uint32_t s = blockIdx.x * 256 + threadIdx.x;
   if (s >= n) return;
@@ -336,7 +337,7 @@ __device__ __forceinline__ void emit_records_body(const uint64_t* __restrict__ s
   const uint32_t cb = cell_base[s], cb_next = cell_base[s + 1];
   if (s == n - 1) {
     root->cells = cb_next;
-    if (cb_next > n) root->overflow = 1;
+    if (cb_next > ccap) root->overflow = 1;
   }
   // leaf: depth = deepest shared level + 1
   const uint32_t leaf_depth = (dn > dp ? dn : dp);  // max(delta_s, delta_{s-1}) + 1, and 0 for a single body
@@ -359,7 +360,7 @@ __device__ __forceinline__ void emit_records_body(const uint64_t* __restrict__ s
     const uint32_t e   = lo;
     const uint32_t cid = cb + q;
     const uint32_t pos = s + cid;
-    if (pos < cap && cid < n) {
+    if (pos < cap && cid < ccap) {
       meta[pos]     = make_uint2((e + 1) + cell_base[e + 1], depth);
       rec_body[pos] = s;
       cell_pos[cid] = pos;
@@ -523,7 +524,8 @@ static int create_impl(nbx_engine* e) {
   e->octree  = s;
   const size_t n = e->n;
   s->nblocks = std::min<uint32_t>((e->n + 255) / 256, uint32_t(e->sm_count) * 8);
-  s->cap     = uint32_t(std::min<uint64_t>(2 * uint64_t(n) + 1, 0xfffffff0ull));
+  s->ccap    = std::max<uint32_t>(e->n, 256u);
+  s->cap     = uint32_t(std::min<uint64_t>(uint64_t(n) + s->ccap + 1, 0xfffffff0ull));
   NBX_CUDA(cudaMalloc(&s->root, sizeof(Root<T>)));
   NBX_CUDA(cudaMemsetAsync(s->root, 0, sizeof(Root<T>), e->stream));
   NBX_CUDA(cudaMalloc(&s->partial, sizeof(T) * 2 * s->nblocks));
@@ -540,8 +542,8 @@ static int create_impl(nbx_engine* e) {
   NBX_CUDA(cudaMalloc(&s->mono, sizeof(vec4_t<T>) * s->cap));
   NBX_CUDA(cudaMalloc(&s->meta, sizeof(uint2) * s->cap));
   NBX_CUDA(cudaMalloc(&s->rec_body, sizeof(uint32_t) * s->cap));
-  NBX_CUDA(cudaMalloc(&s->cell_pos, sizeof(uint32_t) * n));
-  NBX_CUDA(cudaMalloc(&s->cells_by_depth, sizeof(uint32_t) * n));
+  NBX_CUDA(cudaMalloc(&s->cell_pos, sizeof(uint32_t) * s->ccap));
+  NBX_CUDA(cudaMalloc(&s->cells_by_depth, sizeof(uint32_t) * s->ccap));
   NBX_CUDA(cudaMalloc(&s->depth_count, sizeof(uint32_t) * 130));
   NBX_CUDA(cudaMalloc(&s->depth_cursor, sizeof(uint32_t) * 130));
   NBX_CUDA(cudaMalloc(&s->a_sorted, sizeof(vec4_t<T>) * e->n_pad));
@@ -607,16 +609,17 @@ static int build_impl(nbx_engine* e) {
     scan_apply_kernel<<<nb, 1024, 0, e->stream>>>(s->cnt, count, s->blocksum);
     NBX_CUDA(cudaMemsetAsync(s->depth_count, 0, sizeof(uint32_t) * 130, e->stream));
     emit_records_kernel<T, D><<<gb, 256, 0, e->stream>>>(s->skeys, s->deep ? s->skeys_lo : nullptr, s->perm, xm, n, s->delta, s->cnt,
-                                                        s->cap, s->mono, s->meta, s->rec_body, s->cell_pos, s->root, s->depth_count);
+                                                        s->cap, s->ccap, s->mono, s->meta, s->rec_body, s->cell_pos, s->root, s->depth_count);
     e->launches += 4;
   }
   {
     PhaseTimer pt(e, PH_MONO);
     depth_offsets_kernel<<<1, 32, 0, e->stream>>>(s->depth_count, s->depth_cursor);
-    group_cells_kernel<T><<<gb, 256, 0, e->stream>>>(s->cell_pos, s->root, s->meta, s->cap, s->depth_cursor, s->cells_by_depth);
+    const unsigned gc = (s->ccap + 255) / 256;
+    group_cells_kernel<T><<<gc, 256, 0, e->stream>>>(s->cell_pos, s->root, s->meta, s->cap, s->depth_cursor, s->cells_by_depth);
     e->launches += 2;
     for (int depth = (s->deep ? 2 : 1) * KeyTraits<D>::MAXL - 1; depth >= 0; --depth) {
-      monopole_level_kernel<T, D><<<gb, 256, 0, e->stream>>>(s->cells_by_depth, s->depth_count, uint32_t(depth), s->cap, s->mono, s->meta);
+      monopole_level_kernel<T, D><<<gc, 256, 0, e->stream>>>(s->cells_by_depth, s->depth_count, uint32_t(depth), s->cap, s->mono, s->meta);
       e->launches++;
     }
   }
