@@ -370,6 +370,13 @@ def main_nbx(args):
                         "note": ("achieved = requested node bytes (visits x record) / traversal time: an optimistic bound, "
                                  "the records are served mostly from L1/L2; peak = "
                                  + ("MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s"))}
+        try:  # DRAM traffic of the dominant kernel from the committed ncu capture of this exact workload (1 GPU), if any
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(workload_name(args, n))
+            if tr and world == 1:
+                roofline["traffic"] = tr["bytes"]
+                roofline["traffic_source"] = "profiles/" + tr["source"]
+        except (OSError, ValueError):
+            pass
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32" if dt == np.float32 else "f64",
