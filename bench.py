@@ -325,7 +325,7 @@ def main_nbx(args):
                "h2d_bytes_per_step": int(n * (1 + 4 * dim) * isz), "d2h_bytes_per_step": int(n * dim * isz),
                "ms_per_step": 1e3 * e2e_s / args.steps}
 
-    if args.algorithm == "all-pairs" and n >= 65536:
+    if args.algorithm == "all-pairs" and n >= 16384:
         parallelism = f"block-pair units dealt round-robin x{world}, NCCL all-reduce of accelerations"
     elif args.algorithm.startswith("all-pairs"):
         parallelism = f"targets sharded x{world}, NCCL all-gather of positions"
@@ -342,9 +342,9 @@ def main_nbx(args):
             achieved = flops / (ph["force"] * 1e-3) / 1e12 if ph.get("force") else None
             roofline = {"bound": "fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                         "frac": achieved / peak if achieved and peak else None, "traffic": None,
-                        "kernel": "all_pairs_sym_kernel" if (n >= 65536 and args.algorithm == "all-pairs") else "all_pairs_kernel", "kernel_ms": ph.get("force"),
+                        "kernel": "all_pairs_sym_kernel" if (n >= 16384 and args.algorithm == "all-pairs") else "all_pairs_kernel", "kernel_ms": ph.get("force"),
                         "note": f"{FLOP_PER_PAIR[dim]:.0f} algorithmic flop per ORDERED pair x n(n-1)/ranks / force time "
-                                "(pair kernel + partial-sum reduction); for n >= 65536 the kernel evaluates each unordered "
+                                "(pair kernel + partial-sum reduction); for n >= 16384 the kernel evaluates each unordered "
                                 "pair once (Newton's third law, src/all_pairs.h:41-42 TODO) and applies it to both bodies; peak = "
                                 f"{'FFMA' if prec == nbx.F32 else 'DFMA'} microbenchmark measured in this run "
                                 "(MEASURED_PEAKS.json has no FP32/FP64 FMA figure)"}

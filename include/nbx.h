@@ -65,7 +65,7 @@ typedef struct nbx_config {
 #define NBX_FLAG_COLLAPSED_FIX_Z 0x1u /* non-default deviation: also accumulate z in all-pairs-collapsed */
 #define NBX_FLAG_NO_FUSED_INTEGRATE 0x2u /* nbx_step runs force and leapfrog as separate kernels */
 /* all-pairs evaluates each UNORDERED pair once (Newton's third law, the reference's own TODO at src/all_pairs.h:41-42)
- * when n >= 65536; results differ from the ordered sweep only by summation order. These flags override the choice: */
+ * when n >= 16384; results differ from the ordered sweep only by summation order. These flags override the choice: */
 #define NBX_FLAG_ALLPAIRS_ORDERED 0x4u   /* always sweep all ordered pairs (the reference's loop structure) */
 #define NBX_FLAG_ALLPAIRS_SYMMETRIC 0x8u /* use the symmetric kernel for any n */
 

@@ -17,7 +17,6 @@
 // Multi-GPU: units are dealt round-robin to the ranks, the per-rank sums are combined with one ncclAllReduce of the
 // accelerations and every rank integrates all bodies (replicated state, no position exchange).
 #include <cfloat>
-#include <cstdlib>
 
 #include "nbx_device.cuh"
 #include "nbx_internal.cuh"
@@ -294,14 +293,10 @@ static int sym_launch(nbx_engine* e, bool fuse) {
 bool all_pairs_sym_enabled(const nbx_engine* e) {
   if (e->algo != NBX_ALL_PAIRS || (e->cfg.flags & NBX_FLAG_ALLPAIRS_ORDERED)) return false;
   if (e->cfg.flags & NBX_FLAG_ALLPAIRS_SYMMETRIC) return true;
-  return e->n >= 65536;  // below that there are too few (I, J) units to fill 148 SMs
+  return e->n >= 16384;  // measured cross-over on B200; below that there are too few (I, J) units to fill 148 SMs
 }
 
 int all_pairs_sym_force(nbx_engine* e, bool fuse) {
-  static const int var = [] { const char* v = getenv("NBX_SYM_VAR"); return v ? atoi(v) : 0; }();
-  if (e->prec == 4 && e->dim == 3 && var == 1) return sym_launch<float, 3, 4, 3>(e, fuse);
-  if (e->prec == 4 && e->dim == 3 && var == 2) return sym_launch<float, 3, 2, 4>(e, fuse);
-  if (e->prec == 4 && e->dim == 3 && var == 3) return sym_launch<float, 3, 8, 1>(e, fuse);
   if (e->prec == 4) return e->dim == 2 ? sym_launch<float, 2, 4, 2>(e, fuse) : sym_launch<float, 3, 4, 2>(e, fuse);
   return e->dim == 2 ? sym_launch<double, 2, 2, 2>(e, fuse) : sym_launch<double, 3, 2, 2>(e, fuse);
 }
