@@ -24,7 +24,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     orc = O.Oracle(fast=True)
     ok = True
-    for algo, dt, n, dim in (("all-pairs", np.float32, 20011, 3), ("all-pairs", np.float32, 70001, 3), ("all-pairs-collapsed", np.float64, 3001, 3),
+    for algo, dt, n, dim in (("all-pairs", np.float32, 9001, 3), ("all-pairs", np.float32, 70001, 3), ("all-pairs-collapsed", np.float64, 3001, 3),
                              ("bvh", np.float32, 50021, 3), ("octree", np.float64, 40009, 3), ("bvh", np.float64, 7001, 2)):
         s = orc.galaxy(n, dt, dim)
         n = len(s["m"])

@@ -170,7 +170,7 @@ def test_full_size_properties_1M(oracle_fast):
     assert np.abs(f.sum(0)).max() <= 1e-4 * np.abs(f).sum(0).max()
 
 
-# ---- symmetric (Newton's third law) all-pairs: default for n >= 65536, forced here at small n ---------------------------------
+# ---- symmetric (Newton's third law) all-pairs: default for n >= 16384, forced here at small n ---------------------------------
 @pytest.mark.parametrize("tag,dim", CASES, ids=IDS)
 @pytest.mark.parametrize("n", [2, 1001, 4096, 5000])
 def test_symmetric_force_vs_oracle(oracle, oracle_fast, tag, dim, n):
