@@ -475,6 +475,12 @@ static int launch_collapsed(nbx_engine* e) {
 
 int all_pairs_collapsed_force(nbx_engine* e) {
   PhaseTimer pt(e, PH_FORCE);
+  if (all_pairs_sym_enabled(e)) {
+    // large n: the block-pair units of the symmetric kernel ARE the pair-parallel decomposition, with the symmetry the
+    // reference's TODO asks for (all_pairs.h:41-42); the collapsed semantics (2 components, a -= ao reset) live in the finish
+    const int nc = (e->cfg.flags & NBX_FLAG_COLLAPSED_FIX_Z) && e->dim == 3 ? 3 : 2;
+    return all_pairs_sym_force(e, false, nc);
+  }
   if (e->prec == 4) return e->dim == 2 ? launch_collapsed<float, 2>(e) : launch_collapsed<float, 3>(e);
   return e->dim == 2 ? launch_collapsed<double, 2>(e) : launch_collapsed<double, 3>(e);
 }

@@ -189,10 +189,30 @@ __global__ void __launch_bounds__(256, MINB) all_pairs_sym_kernel(SymArgs<T> p) 
   }
 }
 
+// what to do with the summed pair terms (sx, sy, sz) of body b:
+//   nc == 0 : all_pairs_force            a = c * sum                         (all_pairs.h:26), optionally + leapfrog
+//   nc == 2|3: all_pairs_collapsed_force  a[k] = (a[k] - ao[k]) + c * sum[k]  for k < nc  (all_pairs.h:35-39,47-48): the
+//              reference "resets" by subtracting the old acceleration and only touches components 0 and 1 (nc = 2)
+template <typename T, int D>
+__device__ __forceinline__ void sym_store(const LeapArgs<T>& leap, uint32_t b, T sx, T sy, T sz, T c, int fuse, int nc) {
+  if (nc == 0) {
+    const vec4_t<T> anew = make_v4<T>(mul_rn(sx, c), mul_rn(sy, c), D == 3 ? mul_rn(sz, c) : T(0), T(0));
+    leap.a[b] = anew;
+    if (fuse) leapfrog_body<T, D>(leap, b, anew);
+    return;
+  }
+  vec4_t<T> q = leap.a[b];
+  const vec4_t<T> o = leap.ao[b];
+  q.x = add_rn(add_rn(q.x, -o.x), mul_rn(sx, c));
+  q.y = add_rn(add_rn(q.y, -o.y), mul_rn(sy, c));
+  if (nc == 3 && D == 3) q.z = add_rn(add_rn(q.z, -o.z), mul_rn(sz, c));
+  leap.a[b] = q;
+}
+
 // a[b] = c * sum_K P[K][b] (K ascending, only the units this rank computed), optionally fused with the leapfrog
 template <typename T, int D>
 __global__ void __launch_bounds__(256) sym_reduce_kernel(const vec4_t<T>* __restrict__ P, uint64_t slab, uint32_t B, uint32_t K, uint32_t n,
-                                                         uint32_t unit_begin, uint32_t unit_stride, T c, int finish, int fuse,
+                                                         uint32_t unit_begin, uint32_t unit_stride, T c, int finish, int fuse, int nc,
                                                          vec4_t<T>* __restrict__ asum, LeapArgs<T> leap) {
   const uint32_t b = blockIdx.x * 256 + threadIdx.x;
   if (b >= n) return;
@@ -209,20 +229,17 @@ __global__ void __launch_bounds__(256) sym_reduce_kernel(const vec4_t<T>* __rest
     asum[b] = make_v4<T>(sx, sy, D == 3 ? sz : T(0), T(0));
     return;
   }
-  const vec4_t<T> anew = make_v4<T>(mul_rn(sx, c), mul_rn(sy, c), D == 3 ? mul_rn(sz, c) : T(0), T(0));
-  leap.a[b] = anew;
-  if (fuse) leapfrog_body<T, D>(leap, b, anew);
+  sym_store<T, D>(leap, b, sx, sy, sz, c, fuse, nc);
 }
 
 // after the all-reduce of the unscaled sums: scale by c, (optionally) leapfrog
 template <typename T, int D>
-__global__ void __launch_bounds__(256) sym_finish_kernel(const vec4_t<T>* __restrict__ asum, uint32_t n, T c, int fuse, LeapArgs<T> leap) {
+__global__ void __launch_bounds__(256) sym_finish_kernel(const vec4_t<T>* __restrict__ asum, uint32_t n, T c, int fuse, int nc,
+                                                         LeapArgs<T> leap) {
   const uint32_t b = blockIdx.x * 256 + threadIdx.x;
   if (b >= n) return;
-  const vec4_t<T> s    = asum[b];
-  const vec4_t<T> anew = make_v4<T>(mul_rn(s.x, c), mul_rn(s.y, c), D == 3 ? mul_rn(s.z, c) : T(0), T(0));
-  leap.a[b] = anew;
-  if (fuse) leapfrog_body<T, D>(leap, b, anew);
+  const vec4_t<T> s = asum[b];
+  sym_store<T, D>(leap, b, s.x, s.y, s.z, c, fuse, nc);
 }
 
 struct SymState {
@@ -240,7 +257,7 @@ uint32_t all_pairs_sym_block(uint32_t n) {  // B = 1024 * ceil(n / 2^18)  =>  K 
 }
 
 template <typename T, int D, int RI, int MINB>
-static int sym_launch(nbx_engine* e, bool fuse) {
+static int sym_launch(nbx_engine* e, bool fuse, int nc) {
   SymState* s = static_cast<SymState*>(e->sym);
   if (!s) {
     s       = new SymState();
@@ -276,14 +293,14 @@ static int sym_launch(nbx_engine* e, bool fuse) {
   leap.dt = T(e->cfg.dt);
   const unsigned gb = (e->n + 255) / 256;
   if (world == 1) {
-    sym_reduce_kernel<T, D><<<gb, 256, 0, e->stream>>>(p.P, s->slab, s->B, s->K, e->n, 0, 1, T(e->cfg.G), 1, fuse ? 1 : 0,
+    sym_reduce_kernel<T, D><<<gb, 256, 0, e->stream>>>(p.P, s->slab, s->B, s->K, e->n, 0, 1, T(e->cfg.G), 1, fuse ? 1 : 0, nc,
                                                       static_cast<vec4_t<T>*>(s->asum), leap);
     e->launches++;
   } else {
-    sym_reduce_kernel<T, D><<<gb, 256, 0, e->stream>>>(p.P, s->slab, s->B, s->K, e->n, rank, world, T(e->cfg.G), 0, 0,
+    sym_reduce_kernel<T, D><<<gb, 256, 0, e->stream>>>(p.P, s->slab, s->B, s->K, e->n, rank, world, T(e->cfg.G), 0, 0, nc,
                                                       static_cast<vec4_t<T>*>(s->asum), leap);
     NBX_TRY(comm_allreduce_sum(e, s->asum, size_t(e->n) * 4));
-    sym_finish_kernel<T, D><<<gb, 256, 0, e->stream>>>(static_cast<const vec4_t<T>*>(s->asum), e->n, T(e->cfg.G), fuse ? 1 : 0, leap);
+    sym_finish_kernel<T, D><<<gb, 256, 0, e->stream>>>(static_cast<const vec4_t<T>*>(s->asum), e->n, T(e->cfg.G), fuse ? 1 : 0, nc, leap);
     e->launches += 2;
   }
   NBX_CUDA(cudaGetLastError());
@@ -291,14 +308,15 @@ static int sym_launch(nbx_engine* e, bool fuse) {
 }
 
 bool all_pairs_sym_enabled(const nbx_engine* e) {
-  if (e->algo != NBX_ALL_PAIRS || (e->cfg.flags & NBX_FLAG_ALLPAIRS_ORDERED)) return false;
+  if ((e->algo != NBX_ALL_PAIRS && e->algo != NBX_ALL_PAIRS_COLLAPSED) || (e->cfg.flags & NBX_FLAG_ALLPAIRS_ORDERED)) return false;
   if (e->cfg.flags & NBX_FLAG_ALLPAIRS_SYMMETRIC) return true;
   return e->n >= 16384;  // measured cross-over on B200; below that there are too few (I, J) units to fill 148 SMs
 }
 
-int all_pairs_sym_force(nbx_engine* e, bool fuse) {
-  if (e->prec == 4) return e->dim == 2 ? sym_launch<float, 2, 4, 2>(e, fuse) : sym_launch<float, 3, 4, 2>(e, fuse);
-  return e->dim == 2 ? sym_launch<double, 2, 2, 2>(e, fuse) : sym_launch<double, 3, 2, 2>(e, fuse);
+// collapsed_nc: 0 = all_pairs_force semantics; 2 / 3 = all_pairs_collapsed_force semantics over that many components
+int all_pairs_sym_force(nbx_engine* e, bool fuse, int collapsed_nc) {
+  if (e->prec == 4) return e->dim == 2 ? sym_launch<float, 2, 4, 2>(e, fuse, collapsed_nc) : sym_launch<float, 3, 4, 2>(e, fuse, collapsed_nc);
+  return e->dim == 2 ? sym_launch<double, 2, 2, 2>(e, fuse, collapsed_nc) : sym_launch<double, 3, 2, 2>(e, fuse, collapsed_nc);
 }
 
 void all_pairs_sym_destroy(nbx_engine* e) {

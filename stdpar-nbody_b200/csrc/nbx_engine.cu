@@ -240,7 +240,7 @@ int nbx_create(const nbx_config* cfg, nbx_engine** out) {
   // position buffers carry a zero-mass tail (n_pad - n records of padding + one all-pairs tile) so that tile
   // loads never need a bounds check: a zero-mass source contributes exactly 0.
   size_t pos_records = size_t(e->n_pad) + 1024;
-  if (e->algo == NBX_ALL_PAIRS) {  // the symmetric kernel reads whole blocks of B bodies
+  if (e->algo == NBX_ALL_PAIRS || e->algo == NBX_ALL_PAIRS_COLLAPSED) {  // the symmetric kernel reads whole blocks of B bodies
     const size_t B = all_pairs_sym_block(e->n);
     pos_records    = std::max(pos_records, (size_t(e->n) + B - 1) / B * B + 1024);
   }

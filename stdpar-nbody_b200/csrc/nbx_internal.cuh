@@ -149,7 +149,7 @@ int measure_fma_peak(int device, int precision, double* tflops);
 // nbx_allpairs_sym.cu : Newton's-third-law variant of all_pairs_force
 bool all_pairs_sym_enabled(const nbx_engine* e);
 uint32_t all_pairs_sym_block(uint32_t n);
-int all_pairs_sym_force(nbx_engine* e, bool fuse_integrate);
+int all_pairs_sym_force(nbx_engine* e, bool fuse_integrate, int collapsed_nc = 0);
 void all_pairs_sym_destroy(nbx_engine* e);
 // nbx_sort.cu : stable LSD radix sort of (u64 key, u32 value) pairs
 int sorter_create(nbx_engine* e, uint32_t n);

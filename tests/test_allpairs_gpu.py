@@ -218,3 +218,26 @@ def test_both_kernels_at_131072(oracle_fast, flags):
     assert rms(err) <= 5e-5 and err.max() <= 5e-4, (rms(err), err.max())
     f = out["a"].astype(np.float64) * s["m"].astype(np.float64)[:, None]
     assert np.abs(f.sum(0)).max() <= 1e-4 * np.abs(f).sum(0).max()
+
+
+@pytest.mark.parametrize("tag,dim", CASES, ids=IDS)
+def test_collapsed_symmetric_path(oracle_fast, tag, dim):
+    """n >= 16384: all-pairs-collapsed runs on the symmetric block-pair units; same collapsed semantics (components 0,1
+    only, `a -= ao` reset carried), checked against the oracle's collapsed loop on sampled rows."""
+    dt = DT[tag]
+    n = 20000
+    s = oracle_fast.galaxy(n, dt, dim)
+    rng = np.random.default_rng(9)
+    s["a"] = (rng.standard_normal(s["x"].shape) * 1e-5).astype(dt)
+    s["ao"] = s["a"].copy()
+    s["ao"][:, 0] *= dt(0.5)
+    out = run_force(s, "all-pairs-collapsed")
+    ordered = run_force(s, "all-pairs-collapsed", flags=nbx.FLAG_ALLPAIRS_ORDERED)   # the atomics kernel
+    full = oracle_fast.all_pairs_force_truth(s["m"], s["x"], s["G"])
+    want = (s["a"].astype(np.float64) - s["ao"].astype(np.float64))[:, :2] + full[:, :2]
+    tol_rms, tol_max = TOL_A[np.dtype(dt)]
+    for got in (out, ordered):
+        err = rel_err(got["a"][:, :2], want)
+        assert rms(err) <= max(tol_rms, 1e-12) and err.max() <= max(tol_max, 2e-11), (rms(err), err.max())
+    if dim == 3:
+        assert same(out["a"][:, 2], s["a"][:, 2])
