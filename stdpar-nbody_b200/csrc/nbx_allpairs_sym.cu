@@ -316,7 +316,9 @@ bool all_pairs_sym_enabled(const nbx_engine* e) {
 // collapsed_nc: 0 = all_pairs_force semantics; 2 / 3 = all_pairs_collapsed_force semantics over that many components
 int all_pairs_sym_force(nbx_engine* e, bool fuse, int collapsed_nc) {
   if (e->prec == 4) return e->dim == 2 ? sym_launch<float, 2, 4, 2>(e, fuse, collapsed_nc) : sym_launch<float, 3, 4, 2>(e, fuse, collapsed_nc);
-  return e->dim == 2 ? sym_launch<double, 2, 2, 2>(e, fuse, collapsed_nc) : sym_launch<double, 3, 2, 2>(e, fuse, collapsed_nc);
+  // double: 4 targets per thread at one CTA per SM measured 7.6 % faster than 2 targets at two CTAs per SM (the
+  // shuffle butterfly is amortised over twice as many pairs)
+  return e->dim == 2 ? sym_launch<double, 2, 4, 1>(e, fuse, collapsed_nc) : sym_launch<double, 3, 4, 1>(e, fuse, collapsed_nc);
 }
 
 void all_pairs_sym_destroy(nbx_engine* e) {
