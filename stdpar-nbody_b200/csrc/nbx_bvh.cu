@@ -101,20 +101,31 @@ __global__ void __launch_bounds__(256) bbox_partial_kernel(const vec4_t<T>* __re
 // monotone under round-to-nearest, so reducing first and inflating once is exact.
 template <typename T, int D>
 __global__ void bbox_final_kernel(const T* partial, uint32_t nblocks, Box<T>* box) {
-  int k = threadIdx.x;  // one thread per axis
-  if (k >= 3) return;
-  T lo = partial[k], hi = partial[3 + k];
-  for (uint32_t b = 1; b < nblocks; ++b) {
-    lo = tmin(lo, partial[b * 8 + k]);
-    hi = tmax(hi, partial[b * 8 + 3 + k]);
-  }
+  // one warp: lanes stride over the per-CTA partials, then a shuffle reduction (min/max are order-independent => exact)
+  const int lane = threadIdx.x;
+  T lo[3] = {T(0), T(0), T(0)}, hi[3] = {T(0), T(0), T(0)};
+  for (uint32_t b = lane; b < nblocks; b += 32)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      lo[k] = tmin(lo[k], partial[b * 8 + k]);
+      hi[k] = tmax(hi[k], partial[b * 8 + 3 + k]);
+    }
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      lo[k] = tmin(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], off));
+      hi[k] = tmax(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], off));
+    }
+  if (lane >= 3) return;
+  const int k = lane;  // one thread per axis
   const T tol = aabb_tol<T>();
-  lo = tmin(sub_rn(T(0), tol), sub_rn(lo, tol));
-  hi = tmax(add_rn(T(0), tol), add_rn(hi, tol));
+  const T l   = tmin(sub_rn(T(0), tol), sub_rn(lo[k], tol));
+  const T h   = tmax(add_rn(T(0), tol), add_rn(hi[k], tol));
   const T cells = D == 2 ? T(0xffffffffu) : T(0x1fffffu);
-  box->lo[k]   = lo;
-  box->hi[k]   = hi;
-  box->cell[k] = div_rn(sub_rn(hi, lo), cells);
+  box->lo[k]   = l;
+  box->hi[k]   = h;
+  box->cell[k] = div_rn(sub_rn(h, l), cells);
 }
 
 // ---- K11 Hilbert keys ------------------------------------------------------------------------------------------

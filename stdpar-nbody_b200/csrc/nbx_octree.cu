@@ -108,9 +108,15 @@ __global__ void __launch_bounds__(256) bounds_partial_kernel(const vec4_t<T>* __
 
 template <typename T>
 __global__ void bounds_final_kernel(const T* partial, uint32_t nblocks, Root<T>* root) {
-  if (threadIdx.x != 0) return;
+  const int lane = threadIdx.x;  // one warp
   T lo = 0, hi = 0;
-  for (uint32_t b = 0; b < nblocks; ++b) { lo = fmin(lo, partial[2 * b]); hi = fmax(hi, partial[2 * b + 1]); }
+  for (uint32_t b = lane; b < nblocks; b += 32) { lo = fmin(lo, partial[2 * b]); hi = fmax(hi, partial[2 * b + 1]); }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+  }
+  if (lane != 0) return;
   hi = add_rn(hi, T(1));                          // max_size += 1
   lo = sub_rn(lo, T(1));                          // min_size -= 1
   root->x        = div_rn(add_rn(hi, lo), T(2));  // divide
