@@ -350,10 +350,10 @@ static LeapArgs<T> make_leap(nbx_engine* e, bool to_next) {
   return l;
 }
 
-constexpr int AP_TILE   = 512;  // bodies per shared-memory tile (also the zero-mass padding appended to xm)
-constexpr int AP_STAGES = 4;
+constexpr int AP_STAGES = 4;  // TILE (bodies per shared-memory tile) is 512, or 128 for small n (more CTAs); the position
+                              // buffers carry >= 1024 zero-mass padding records, so whole tiles can always be loaded
 
-template <typename T, int D, int TI, int BLOCK, int MINB>
+template <typename T, int D, int TI, int BLOCK, int MINB, int AP_TILE>
 static int launch_all_pairs_cfg(nbx_engine* e, bool fuse, uint32_t nsplit, uint32_t tiles_per_split) {
   auto kern = all_pairs_kernel<T, D, TI, BLOCK, AP_TILE, AP_STAGES, MINB>;
   const size_t smem = size_t(AP_STAGES) * AP_TILE * sizeof(vec4_t<T>) + AP_STAGES * sizeof(uint64_t);
@@ -396,7 +396,7 @@ static int launch_all_pairs_cfg(nbx_engine* e, bool fuse, uint32_t nsplit, uint3
   return NBX_OK;
 }
 
-template <typename T, int D>
+template <typename T, int D, int AP_TILE>
 static int launch_all_pairs(nbx_engine* e, bool fuse) {
   const uint32_t nt = e->te - e->tb;
   if (nt == 0) return NBX_OK;
@@ -417,12 +417,12 @@ static int launch_all_pairs(nbx_engine* e, bool fuse) {
   uint32_t tps = (tiles_total + nsplit - 1) / nsplit;
   nsplit       = (tiles_total + tps - 1) / tps;
   if constexpr (sizeof(T) == 4) {
-    if (ti == 4) return launch_all_pairs_cfg<T, D, 4, 256, 3>(e, fuse, nsplit, tps);
-    if (ti == 2) return launch_all_pairs_cfg<T, D, 2, 256, 3>(e, fuse, nsplit, tps);
-    return launch_all_pairs_cfg<T, D, 1, 256, 3>(e, fuse, nsplit, tps);
+    if (ti == 4) return launch_all_pairs_cfg<T, D, 4, 256, 3, AP_TILE>(e, fuse, nsplit, tps);
+    if (ti == 2) return launch_all_pairs_cfg<T, D, 2, 256, 3, AP_TILE>(e, fuse, nsplit, tps);
+    return launch_all_pairs_cfg<T, D, 1, 256, 3, AP_TILE>(e, fuse, nsplit, tps);
   } else {
-    if (ti == 2) return launch_all_pairs_cfg<T, D, 2, 256, 2>(e, fuse, nsplit, tps);
-    return launch_all_pairs_cfg<T, D, 1, 256, 2>(e, fuse, nsplit, tps);
+    if (ti == 2) return launch_all_pairs_cfg<T, D, 2, 256, 2, AP_TILE>(e, fuse, nsplit, tps);
+    return launch_all_pairs_cfg<T, D, 1, 256, 2, AP_TILE>(e, fuse, nsplit, tps);
   }
 }
 
@@ -434,8 +434,14 @@ int all_pairs_force(nbx_engine* e, bool fuse_integrate) {
     if (rc == NBX_OK && fuse_integrate) e->cur ^= 1;
     return rc;
   }
-  if (e->prec == 4) rc = e->dim == 2 ? launch_all_pairs<float, 2>(e, fuse_integrate) : launch_all_pairs<float, 3>(e, fuse_integrate);
-  else rc = e->dim == 2 ? launch_all_pairs<double, 2>(e, fuse_integrate) : launch_all_pairs<double, 3>(e, fuse_integrate);
+  const bool small = e->n < 32768;  // 128-body tiles give small problems 4x more CTAs to spread over the 148 SMs
+  if (e->prec == 4) {
+    if (e->dim == 2) rc = small ? launch_all_pairs<float, 2, 128>(e, fuse_integrate) : launch_all_pairs<float, 2, 512>(e, fuse_integrate);
+    else rc = small ? launch_all_pairs<float, 3, 128>(e, fuse_integrate) : launch_all_pairs<float, 3, 512>(e, fuse_integrate);
+  } else {
+    if (e->dim == 2) rc = small ? launch_all_pairs<double, 2, 128>(e, fuse_integrate) : launch_all_pairs<double, 2, 512>(e, fuse_integrate);
+    else rc = small ? launch_all_pairs<double, 3, 128>(e, fuse_integrate) : launch_all_pairs<double, 3, 512>(e, fuse_integrate);
+  }
   if (rc == NBX_OK && fuse_integrate) e->cur ^= 1;
   return rc;
 }
