@@ -127,6 +127,14 @@ int nbx_octree_get_root(nbx_engine* e, void* side, void* root_x, uint64_t* nodes
 int nbx_octree_get_canonical(nbx_engine* e, uint64_t* count, uint32_t* depth, uint64_t* path, uint32_t* kind,
                              void* monopole);
 
+/* ---- Saver streaming: positions.bin frames without stalling the GPU (replaces Saver::save_points, src/saving.h:110-114) ----
+ * nbx_stream_positions_begin snapshots the CURRENT positions (after all steps issued so far) and starts an asynchronous
+ * device->pinned-host copy on a second stream; it returns immediately and the copy overlaps the following nbx_step calls.
+ * At most two snapshots can be in flight. nbx_stream_positions_end waits for the OLDEST snapshot in flight and copies it
+ * (packed vec<T,N>[n], the layout of positions.bin frames) to x_host. */
+int nbx_stream_positions_begin(nbx_engine* e);
+int nbx_stream_positions_end(nbx_engine* e, void* x_host);
+
 /* ---- multi-GPU plumbing (one process per GPU; rendezvous is the caller's, e.g. torch.distributed) ---------- */
 #define NBX_UNIQUE_ID_BYTES 128
 int nbx_comm_unique_id(void* id128);

@@ -1,6 +1,5 @@
 // nbx_engine.cu — engine lifetime, host<->device state transfer, step drivers and the extern "C" surface of nbx.h.
 #include <cstring>
-#include <mutex>
 
 #include "nbx_internal.cuh"
 
@@ -126,6 +125,46 @@ static int download_impl(nbx_engine* e, void* m, void* x, void* v, void* a, void
     NBX_TRY(get(dsth[q], sizeof(T) * size_t(n) * D));
   }
   NBX_CUDA(cudaGetLastError());
+  return NBX_OK;
+}
+
+// ---- Saver streaming ------------------------------------------------------------------------------------------------
+template <typename T, int D>
+static int stream_begin_impl(nbx_engine* e) {
+  if (e->snap_count == 2) return fail(NBX_ERR_STATE, "two position snapshots already in flight: call nbx_stream_positions_end first");
+  const size_t bytes = sizeof(T) * size_t(e->n) * D;
+  if (!e->copy_stream) {
+    NBX_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+      NBX_CUDA(cudaMalloc(&e->snap_dev[k], bytes));
+      NBX_CUDA(cudaMallocHost(&e->snap_host[k], bytes));
+      NBX_CUDA(cudaEventCreateWithFlags(&e->snap_ready[k], cudaEventDisableTiming));
+      NBX_CUDA(cudaEventCreateWithFlags(&e->snap_done[k], cudaEventDisableTiming));
+    }
+  }
+  const int slot = (e->snap_head + e->snap_count) % 2;
+  // the (cheap, HBM-bound) unpack runs on the main stream, so later steps may overwrite the positions freely; the slow
+  // PCIe copy runs on the copy stream and overlaps them
+  unpack_vec_kernel<T, D><<<(e->n + 255) / 256, 256, 0, e->stream>>>((const vec4_t<T>*)e->xm[e->cur], (T*)e->snap_dev[slot], e->n);
+  e->launches++;
+  NBX_CUDA(cudaEventRecord(e->snap_ready[slot], e->stream));
+  NBX_CUDA(cudaStreamWaitEvent(e->copy_stream, e->snap_ready[slot], 0));
+  NBX_CUDA(cudaMemcpyAsync(e->snap_host[slot], e->snap_dev[slot], bytes, cudaMemcpyDeviceToHost, e->copy_stream));
+  NBX_CUDA(cudaEventRecord(e->snap_done[slot], e->copy_stream));
+  e->d2h += bytes;
+  e->snap_count++;
+  return NBX_OK;
+}
+
+template <typename T, int D>
+static int stream_end_impl(nbx_engine* e, void* x_host) {
+  if (e->snap_count == 0) return fail(NBX_ERR_STATE, "no position snapshot in flight");
+  if (!x_host) return fail(NBX_ERR_INVALID, "x_host is NULL");
+  const int slot = e->snap_head;
+  NBX_CUDA(cudaEventSynchronize(e->snap_done[slot]));
+  memcpy(x_host, e->snap_host[slot], sizeof(T) * size_t(e->n) * D);
+  e->snap_head = (e->snap_head + 1) % 2;
+  e->snap_count--;
   return NBX_OK;
 }
 
@@ -275,7 +314,13 @@ int nbx_destroy(nbx_engine* e) {
   void* bufs[] = {e->xm[0], e->xm[1], e->v, e->a, e->ao, e->v_alt, e->a_alt, e->ao_alt, e->partial, e->tickets, e->stage};
   for (void* b : bufs)
     if (b) cudaFree(b);
-  if (e->pinned) cudaFreeHost(e->pinned);
+  for (int k = 0; k < 2; ++k) {
+    if (e->snap_dev[k]) cudaFree(e->snap_dev[k]);
+    if (e->snap_host[k]) cudaFreeHost(e->snap_host[k]);
+    if (e->snap_ready[k]) cudaEventDestroy(e->snap_ready[k]);
+    if (e->snap_done[k]) cudaEventDestroy(e->snap_done[k]);
+  }
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   for (int s = 0; s < PH_COUNT; ++s)
     for (int k = 0; k < 2; ++k)
       if (e->ph_ev[s][k]) cudaEventDestroy(e->ph_ev[s][k]);
@@ -298,6 +343,15 @@ int nbx_upload(nbx_engine* e, const void* m, const void* x, const void* v, const
 int nbx_download(nbx_engine* e, void* m, void* x, void* v, void* a, void* ao) {
   NBX_ENTER(e);
   return NBX_DISPATCH(e, download_impl, e, m, x, v, a, ao);
+}
+
+int nbx_stream_positions_begin(nbx_engine* e) {
+  NBX_ENTER(e);
+  return NBX_DISPATCH(e, stream_begin_impl, e);
+}
+int nbx_stream_positions_end(nbx_engine* e, void* x_host) {
+  NBX_ENTER(e);
+  return NBX_DISPATCH(e, stream_end_impl, e, x_host);
 }
 
 int nbx_step(nbx_engine* e, uint32_t steps) {

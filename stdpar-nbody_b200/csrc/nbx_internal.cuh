@@ -86,8 +86,13 @@ struct nbx_engine {
   // host<->device staging for upload/download (AoS <-> vec4 conversion happens on the device)
   void* stage = nullptr;
   size_t stage_bytes = 0;
-  void* pinned = nullptr;
-  size_t pinned_bytes = 0;
+  // Saver streaming: two snapshots in flight (device staging + pinned host buffer + "copy done" event each)
+  cudaStream_t copy_stream = nullptr;
+  void* snap_dev[2]        = {nullptr, nullptr};
+  void* snap_host[2]       = {nullptr, nullptr};
+  cudaEvent_t snap_ready[2] = {nullptr, nullptr};  // unpack kernel finished on the main stream
+  cudaEvent_t snap_done[2]  = {nullptr, nullptr};  // D2H finished on the copy stream
+  int snap_head = 0, snap_count = 0;               // ring of pending snapshots
 
   // tree state lives in opaque per-algorithm blocks owned by nbx_bvh.cu / nbx_octree.cu
   void* bvh = nullptr;

@@ -364,6 +364,29 @@ struct Saver {
       fen.write(reinterpret_cast<const char*>(hdr), sizeof(hdr));
     }
   }
+  // Streaming variant for the per-step frames: `begin` snapshots the positions and starts the device->host copy on a
+  // second stream (overlapping the next step), `flush` writes the oldest pending frame to positions.bin.
+  int pending = 0;
+  void begin_frame(Engines<T, N>& eng) {
+    if (!pos) return;
+    if (pending == 2) flush_frame(eng);
+    check(nbx_stream_positions_begin(eng.e[0]), "nbx_stream_positions_begin");
+    ++pending;
+  }
+  void flush_frame(Engines<T, N>& eng) {
+    if (!pos || pending == 0) return;
+    check(nbx_stream_positions_end(eng.e[0], eng.sys.x.data()), "nbx_stream_positions_end");
+    fpos.write(reinterpret_cast<const char*>(eng.sys.x.data()), std::streamsize(n) * data_size * N);
+    --pending;
+  }
+  void save_energy_only(Engines<T, N>& eng) {
+    if (!energy) return;
+    double k = 0, g = 0;
+    check(nbx_calc_energies(eng.e[0], &k, &g), "nbx_calc_energies");
+    T kt = T(k), gt = T(g);
+    fen.write(reinterpret_cast<const char*>(&kt), sizeof(T));
+    fen.write(reinterpret_cast<const char*>(&gt), sizeof(T));
+  }
   void save_all(Engines<T, N>& eng, bool state_is_current) {
     if (!pos && !energy) return;
     if (pos) {
@@ -436,8 +459,12 @@ void run_algorithm(HostSystem<T, N>& sys, Options o) {
           for (T mi : sys.m) total_mass += mi;
           std::cout << std::format("Total mass: {: .5f}\n", total_mass);
         }
-        saver.save_all(eng, false);
+        // frame k is copied to the host while step k+1 runs (src/saving.h:110-114 writes it synchronously)
+        saver.begin_frame(eng);
+        saver.save_energy_only(eng);
+        if (saver.pending == 2) saver.flush_frame(eng);
       }
+      while (saver.pending) saver.flush_frame(eng);
     });
   } else {
     eng.step(std::uint32_t(o.warmup_steps));

@@ -31,7 +31,8 @@ SYMBOLS = [
     "nbx_step", "nbx_step_timed", "nbx_sync", "nbx_all_pairs_force", "nbx_all_pairs_collapsed_force",
     "nbx_accelerate_step", "nbx_calc_energies", "nbx_bvh_bounding_box", "nbx_bvh_hilbert_sort", "nbx_bvh_build_tree",
     "nbx_bvh_compute_force", "nbx_bvh_get_keys", "nbx_bvh_get_nodes", "nbx_octree_build", "nbx_octree_compute_force",
-    "nbx_octree_get_root", "nbx_octree_get_canonical", "nbx_comm_unique_id", "nbx_comm_init_rank",
+    "nbx_octree_get_root", "nbx_octree_get_canonical", "nbx_stream_positions_begin", "nbx_stream_positions_end",
+    "nbx_comm_unique_id", "nbx_comm_init_rank",
     "nbx_measure_fma_peak", "nbx_traversal_stats", "nbx_get_counters", "nbx_set_phase_timing", "nbx_get_phase_ms",
 ]
 
@@ -216,6 +217,15 @@ class Engine:
         mono = np.empty((k, self.dim + 1), self.dtype)
         _check(lib().nbx_octree_get_canonical(self._h, C.byref(cnt), _p(depth), _p(path), _p(kind), _p(mono)))
         return depth, path, kind, mono
+
+    # ---- Saver streaming (src/saving.h:110-114) -------------------------------------------------------------------
+    def stream_positions_begin(self):
+        _check(lib().nbx_stream_positions_begin(self._h))
+
+    def stream_positions_end(self):
+        x = np.empty((self.n, self.dim), self.dtype)
+        _check(lib().nbx_stream_positions_end(self._h, _p(x)))
+        return x
 
     # ---- multi-GPU ----------------------------------------------------------------------------------------------
     def comm_init_rank(self, unique_id: bytes):

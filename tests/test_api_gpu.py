@@ -81,3 +81,30 @@ def test_tiny_systems(oracle, algo, n):
     ref = oracle.run(algo, s, 2)
     assert np.isfinite(out["x"]).all()
     assert np.allclose(out["x"], ref["x"], rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("algo,dt", [("all-pairs", np.float32), ("octree", np.float64), ("bvh", np.float32)])
+def test_streamed_position_frames_equal_synchronous_downloads(oracle, algo, dt):
+    """nbx_stream_positions_begin/end (Saver streaming): frames copied while the next steps run are bit-identical to the
+    frames a synchronous nbx_download returns after the same steps."""
+    s = oracle.galaxy(20000, dt, 3)
+    with nbx.Engine(20000, 3, dt, algo, s["dt"], s["G"]) as e:
+        e.upload_state(s)
+        want = []
+        for _ in range(5):
+            e.step(1)
+            want.append(e.download(("x",))["x"])
+    with nbx.Engine(20000, 3, dt, algo, s["dt"], s["G"]) as e:
+        e.upload_state(s)
+        got = []
+        for k in range(5):
+            e.step(1)
+            e.stream_positions_begin()          # frame k in flight while step k+1 runs
+            if k >= 1:
+                got.append(e.stream_positions_end())
+        got.append(e.stream_positions_end())
+        with pytest.raises(nbx.NbxError):
+            e.stream_positions_end()            # nothing left in flight
+    assert len(got) == 5
+    for a, b in zip(got, want):
+        assert same(a, b)
