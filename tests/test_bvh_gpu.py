@@ -160,3 +160,32 @@ def test_traversal_stats_match_oracle_visits(oracle_fast):
         st = e.traversal_stats()
     assert st["node_visits"] == visits
     assert st["warp_steps"] * 32 >= st["node_visits"] and st["interactions"] <= st["node_visits"]
+
+
+def test_bvh_full_pipeline_4M(oracle):
+    """A BASELINE-scale run (n = 4M, 3-D float): keys and permutation bit-exact against the pinned oracle, root node =
+    total mass / centre of mass, and the traversal of 1000 sampled (sorted) bodies against the oracle's walk."""
+    n = 4_000_000
+    s = oracle.galaxy(n, np.float32, 3)
+    with engine(s) as e:
+        lo, hi = e.bounding_box()
+        e.hilbert_sort()
+        keys, perm = e.bvh_keys()
+        e.build_tree()
+        e.bvh_compute_force()
+        out = e.download()
+        st = e.traversal_stats()
+    olo, ohi = oracle.bbox(s["x"])
+    assert same(lo, olo) and same(hi, ohi)
+    okeys = oracle.keys(s["x"], olo, ohi)
+    assert same(keys, okeys), "Hilbert keys must be bit-exact at scale"
+    assert same(perm, oracle.sort_perm(okeys))
+    assert same(out["x"], s["x"][perm]) and same(out["m"], s["m"][perm])
+    nm, bw, _ = oracle.bvh_build(out["m"], out["x"])
+    rng = np.random.default_rng(3)
+    targets = np.sort(rng.choice(n, 1000, replace=False)).astype(np.uint32)
+    ref, visits = oracle.bvh_force(out["m"], out["x"], nm, bw, s["G"], THETA, targets=targets)
+    err = rel_err(out["a"][targets], ref)
+    assert rms(err) <= 2e-5 and err.max() <= 5e-4, (rms(err), err.max())
+    assert abs(st["node_visits"] / n - visits / len(targets)) < 0.1 * visits / len(targets)
+    assert np.isfinite(out["a"]).all()
