@@ -87,3 +87,72 @@ def test_five_steps_vs_oracle(oracle_fast, name, algo):
     tol = 2e-4 if s["x"].dtype == np.float32 else 1e-9
     scale = np.abs(ref["x"]).max()
     assert np.abs(out["x"].astype(np.float64) - ref["x"]).max() <= tol * scale
+
+
+# ---- degenerate geometries: the integer artefacts must stay bit-exact ---------------------------------------------------------
+def _state(x, dt):
+    x = np.ascontiguousarray(x, dt)
+    n = len(x)
+    rng = np.random.default_rng(11)
+    return dict(m=(rng.random(n) + 0.5).astype(dt), x=x, v=np.zeros_like(x), a=np.zeros_like(x), ao=np.zeros_like(x),
+                dt=dt(0.01), G=dt(1.0))
+
+
+def _geometries(dt, dim):
+    rng = np.random.default_rng(5)
+    n = 3000
+    line = np.zeros((n, dim)); line[:, 0] = np.linspace(-7, 13, n)                  # zero extent in the other axes
+    plane = rng.random((n, dim)) * 50; plane[:, -1] = 3.25                           # one flat axis
+    far = rng.random((n, dim)) * 1e-3 + 1e4                                          # tiny cloud far from the origin
+    big = (rng.random((n, dim)) - 0.5) * 2e6                                         # huge coordinates
+    clusters = np.concatenate([rng.standard_normal((n // 2, dim)) * 1e-2 - 40, rng.standard_normal((n - n // 2, dim)) * 5 + 60])
+    return {"line": line, "plane": plane, "far-cloud": far, "huge": big, "two-clusters": clusters}
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_degenerate_geometries_bvh_and_octree(oracle, oracle_fast, dt, dim):
+    for name, x in _geometries(dt, dim).items():
+        s = _state(x, dt)
+        if len(np.unique(s["x"], axis=0)) != len(s["x"]):
+            continue  # rounding to dt made coincident bodies: the octree would (correctly) report them
+        n = len(s["m"])
+        # BVH: keys, permutation, nodes
+        lo, hi = oracle.bbox(s["x"])
+        keys = oracle.keys(s["x"], lo, hi)
+        perm = oracle.sort_perm(keys)
+        so = oracle.permute(perm, s)
+        nm, bw, b = oracle.bvh_build(so["m"], so["x"])
+        with nbx.Engine(n, dim, dt, "bvh", s["dt"], s["G"], theta=0.5) as e:
+            e.upload_state(s)
+            glo, ghi = e.bounding_box()
+            e.hilbert_sort()
+            gkeys, gperm = e.bvh_keys()
+            e.build_tree()
+            gm, gbw, gb = e.bvh_nodes()
+            e.bvh_compute_force()
+            a = e.download(("a",))["a"]
+        assert same(glo, lo) and same(ghi, hi), name
+        assert same(gkeys, keys) and same(gperm, perm), name
+        assert same(gm, nm) and same(gbw, bw) and same(gb, b), name
+        ref, _ = oracle_fast.bvh_force(so["m"], so["x"], nm, bw, s["G"], 0.5)
+        assert rms(rel_err(a, ref)) <= (5e-5 if dt == np.float32 else 1e-12), name
+        # octree: canonical topology + monopoles
+        try:
+            t = oracle.octree_build(s["m"], s["x"])
+        except RuntimeError:
+            continue  # deeper than the reference's own node capacity allows
+        depth, path, kind, mo = oracle.octree_canonical(t, dim)
+        with nbx.Engine(n, dim, dt, "octree", s["dt"], s["G"], theta=0.5) as e:
+            e.upload_state(s)
+            try:
+                e.octree_build()
+            except nbx.NbxError as ex:
+                assert ex.code == -4, name   # only "more levels than two key words hold" may be refused
+                continue
+            gd, gp, gk, gmo = e.octree_canonical()
+            e.octree_compute_force()
+            a = e.download(("a",))["a"]
+        assert same(gd, depth) and same(gk, kind) and same(gmo, mo), name
+        ref, _ = oracle_fast.octree_force(s["x"], t, s["G"], 0.5)
+        assert rms(rel_err(a, ref)) <= (5e-5 if dt == np.float32 else 1e-12), name
