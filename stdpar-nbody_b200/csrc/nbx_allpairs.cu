@@ -94,13 +94,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) all_pairs_kernel(AllPairsArgs<T> 
       for (int t = 0; t < TI; ++t) {
         T dx = b.x - xi[t];
         T dy = b.y - yi[t];
-        T d2 = fma(dy, dy, dx * dx);
+        T d2 = fma(dy, dy, sq_plus_tiny(dx));
         T dz = T(0);
         if (D == 3) {
           dz = b.z - zi[t];
           d2 = fma(dz, dz, d2);
         }
-        T s   = b.w * inv_dist3(d2);
+        T s   = b.w * inv_dist3_pos(d2);
         ax[t] = fma(dx, s, ax[t]);
         ay[t] = fma(dy, s, ay[t]);
         if (D == 3) az[t] = fma(dz, s, az[t]);
@@ -211,13 +211,13 @@ __global__ void __launch_bounds__(256) collapsed_kernel(CollapsedArgs<T> p) {
         const V4 ri = rows[warp * ROWS + r];  // broadcast
         T dx = b.x - ri.x;
         T dy = b.y - ri.y;
-        T d2 = fma(dy, dy, dx * dx);
+        T d2 = fma(dy, dy, sq_plus_tiny(dx));
         T dz = T(0);
         if (D == 3) {
           dz = b.z - ri.z;
           d2 = fma(dz, dz, d2);
         }
-        T s       = b.w * inv_dist3(d2);
+        T s       = b.w * inv_dist3_pos(d2);
         acc[r][0] = fma(dx, s, acc[r][0]);
         acc[r][1] = fma(dy, s, acc[r][1]);
         if (NC == 3) acc[r][2] = fma(dz, s, acc[r][2]);

@@ -102,10 +102,10 @@ __global__ void __launch_bounds__(256, MINB) all_pairs_sym_kernel(SymArgs<T> p) 
 #pragma unroll
           for (int t = 0; t < RI; ++t) {
             T dx = b.x - xi[t], dy = b.y - yi[t];
-            T d2 = fma(dy, dy, dx * dx);
+            T d2 = fma(dy, dy, sq_plus_tiny(dx));
             T dz = T(0);
             if (D == 3) { dz = b.z - zi[t]; d2 = fma(dz, dz, d2); }
-            T s   = b.w * inv_dist3(d2);
+            T s   = b.w * inv_dist3_pos(d2);
             ax[t] = fma(dx, s, ax[t]);
             ay[t] = fma(dy, s, ay[t]);
             if (D == 3) az[t] = fma(dz, s, az[t]);
@@ -122,10 +122,10 @@ __global__ void __launch_bounds__(256, MINB) all_pairs_sym_kernel(SymArgs<T> p) 
 #pragma unroll
             for (int t = 0; t < RI; ++t) {
               T dx = b.x - xi[t], dy = b.y - yi[t];
-              T d2 = fma(dy, dy, dx * dx);
+              T d2 = fma(dy, dy, sq_plus_tiny(dx));
               T dz = T(0);
               if (D == 3) { dz = b.z - zi[t]; d2 = fma(dz, dz, d2); }
-              const T inv = inv_dist3(d2);
+              const T inv = inv_dist3_pos(d2);
               const T si = b.w * inv, sj = mi[t] * inv;
               ax[t] = fma(dx, si, ax[t]);
               ay[t] = fma(dy, si, ay[t]);

@@ -39,6 +39,23 @@ __device__ __forceinline__ double rcp_fast(double x) {
 }
 __device__ __forceinline__ double inv_dist3(double d2) { return rcp_fast(fma(d2, sqrt_fast(d2), DBL_EPSILON)); }
 
+// All-pairs inner loops: in double d2 is formed as (dx*dx + 1e-300) + dy*dy (+ dz*dz) — the addend rides on the first FMA for free
+// and keeps d2 > 0, so the double path needs no fmax guard in front of the rsqrt seed. 1e-300 is far below the rounding
+// of any non-zero d2; for a self / coincident pair it gives den = eps exactly as d2 = 0 does, and the pair still
+// contributes m * 0 * (1/eps) = 0.
+__device__ __forceinline__ float sq_plus_tiny(float dx) { return dx * dx; }  // float: MUFU.SQRT(0) = 0 needs no guard
+__device__ __forceinline__ double sq_plus_tiny(double dx) { return fma(dx, dx, 1e-300); }
+__device__ __forceinline__ float inv_dist3_pos(float d2) { return inv_dist3(d2); }
+__device__ __forceinline__ double inv_dist3_pos(double d2) {  // requires d2 > 0
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d2));
+  const double t = d2 * y;
+  const double e = fma(-t, y, 1.0);
+  const double q = e * fma(0.375, e, 0.5);
+  y              = fma(y, q, y);
+  return rcp_fast(fma(d2, d2 * y, DBL_EPSILON));
+}
+
 // ---- octree form: dx = sqrt(d2) + eps ; 1/dx^3   (vec.h:243-246 dist, octree.h:240-242) ---------------------------------
 __device__ __forceinline__ float dist_eps(float d2) {
   float sq;
@@ -46,6 +63,17 @@ __device__ __forceinline__ float dist_eps(float d2) {
   return sq + FLT_EPSILON;
 }
 __device__ __forceinline__ double dist_eps(double d2) { return sqrt_fast(d2) + DBL_EPSILON; }
+// same with d2 > 0 guaranteed by sq_plus_tiny (sqrt(1e-300) + eps == eps exactly, like the reference's 0 + eps)
+__device__ __forceinline__ float dist_eps_pos(float d2) { return dist_eps(d2); }
+__device__ __forceinline__ double dist_eps_pos(double d2) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d2));
+  const double t = d2 * y;
+  const double e = fma(-t, y, 1.0);
+  const double q = e * fma(0.375, e, 0.5);
+  y              = fma(y, q, y);
+  return fma(d2, y, DBL_EPSILON);
+}
 __device__ __forceinline__ float inv_cube(float dx) {
   float inv;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(dx * dx * dx));

@@ -467,9 +467,9 @@ __global__ void __launch_bounds__(128) octree_force_kernel(const vec4_t<T>* __re
     const vec4_t<T> nm = mono[p];  // warp-uniform address
     const uint2 me     = meta[p];
     const T dx_ = nm.x - xs.x, dy_ = nm.y - xs.y, dz_ = D == 3 ? nm.z - xs.z : T(0);
-    T d2 = fma(dy_, dy_, dx_ * dx_);
+    T d2 = fma(dy_, dy_, sq_plus_tiny(dx_));
     if (D == 3) d2 = fma(dz_, dz_, d2);
-    const T dx      = dist_eps(d2);
+    const T dx      = dist_eps_pos(d2);
     const bool act  = p >= resume;
     const bool take = (me.y & LEAF_FLAG) || (side_at(root_side, me.y & 0xff) < theta * dx);
     if (COUNT) { n_visit += act; n_take += act && take; n_step += 1; }
