@@ -358,26 +358,37 @@ __global__ void __launch_bounds__(128) bvh_force_kernel(const vec4_t<T>* __restr
 // smallest (covered, level) key over its lanes with one REDUX.MIN, loads THAT node once (warp-uniform address), and only
 // the lanes that asked for it act on it. The warp therefore walks the union of its lanes' paths in leaf order; each lane
 // performs exactly the reference's sequence of tests and interactions.
+//
+// The per-lane state is folded into ONE word. `covered` is always even (nodes cover >= 2 leaves, the
+// body level covers 2), so key = (covered << 4) | level holds covered <= 2^27 without overflow. The key only ever grows:
+// opening node (covered, level) goes to (covered, level + 1) = key + 1 — which no other lane can be below, so the update
+// is key = max(key, candidate) with a warp-uniform candidate and needs no "is this my node" masking — and accepting adds
+// 2^(levels-level) leaves minus one level for a right child (sibling for a left child). The acceptance test is evaluated
+// by every lane (the node loads are warp-uniform anyway); only the accumulation is predicated. A lane is finished when
+// covered >= n, i.e. key >= nlim; the warp stops when the minimum is.
 template <typename T, int D, bool COUNT = false>
-__global__ void __launch_bounds__(128) bvh_force_warp_kernel(const vec4_t<T>* __restrict__ xm, const vec4_t<T>* __restrict__ node_m,
-                                                             const T* __restrict__ bw, uint32_t n, uint32_t tb, uint32_t te,
-                                                             uint32_t levels, T theta2, T c, vec4_t<T>* __restrict__ a_out,
-                                                             unsigned long long* stats = nullptr) {
-  const uint32_t i     = tb + blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid     = i < te;
-  const vec4_t<T> xs   = xm[valid ? i : tb];
+__global__ void __launch_bounds__(128) bvh_force_key_kernel(const vec4_t<T>* __restrict__ xm, const vec4_t<T>* __restrict__ node_m1,
+                                                            const T* __restrict__ bw1, uint32_t n, uint32_t tb, uint32_t te,
+                                                            uint32_t levels, T theta2, T c, vec4_t<T>* __restrict__ a_out,
+                                                            unsigned long long* stats = nullptr) {
+  // node_m1 / bw1 are the node arrays offset by -1 element: indexed by the 1-based heap index kk = k + 1
+  const uint32_t i   = tb + blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid   = i < te;
+  const vec4_t<T> xs = xm[valid ? i : tb];
   unsigned long long n_visit = 0, n_take = 0, n_step = 0;  // COUNT only
-  constexpr uint32_t DONE = 0xffffffffu;
-  uint32_t covered = 0, level = 0;
-  uint32_t key     = valid ? 0u : DONE;  // (covered << 5) | level
+  const uint32_t nlim = (n + (n & 1u)) << 4;  // covered is even: covered >= n  <=>  covered >= n rounded up to even
+  const uint32_t sent = 16u << levels;        // one above the largest active covered << 4
+  const uint32_t lv4  = levels + 4;
+  uint32_t key = valid ? 0u : 0xffffffffu;
   T ax = 0, ay = 0, az = 0;
   for (;;) {
     const uint32_t kmin = __reduce_min_sync(0xffffffffu, key);
-    if (kmin == DONE) break;
-    const uint32_t cl = kmin & 31u, cpos = kmin >> 5;
+    if (kmin >= nlim) break;
+    const uint32_t cl = kmin & 31u;
     const bool act    = key == kmin;
     if (COUNT) { n_visit += act; n_step += 1; }
     if (cl == levels) {  // body level: the two bodies cpos, cpos+1 (bvh.h:288-303)
+      const uint32_t cpos = (kmin >> 4) & ~1u;
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const uint32_t bidx = cpos + q;
@@ -394,34 +405,30 @@ __global__ void __launch_bounds__(128) bvh_force_warp_kernel(const vec4_t<T>* __
           }
         }
       }
-      if (act) {
-        covered += 2;
-        level -= 1;
-        if (COUNT) n_take += 1;
-      }
+      if (act) key = kmin + (cl ? 31u : 32u);  // covered += 2, level -= 1 (n = 1: the body level is level 0)
+      if (COUNT) n_take += act;
     } else {
-      const uint32_t k   = ((1u << cl) - 1) + (cpos >> (levels - cl));
-      const vec4_t<T> nm = node_m[k];
-      const T w          = bw[k];
-      if (act) {
-        // (xj - xs) == -(xs - xj) exactly, so one difference serves the reference-order dist2 and the accumulation
-        const T dx = sub_rn(nm.x, xs.x), dy = sub_rn(nm.y, xs.y), dz = D == 3 ? sub_rn(nm.z, xs.z) : T(0);
-        T d2 = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
-        if (D == 3) d2 = add_rn(d2, mul_rn(dz, dz));
-        if (mul_rn(w, w) < mul_rn(theta2, d2)) {
-          T s = nm.w * inv_dist3(d2);
-          ax = fma(dx, s, ax);
-          ay = fma(dy, s, ay);
-          if (D == 3) az = fma(dz, s, az);
-          covered += 1u << (levels - cl);
-          if (COUNT) n_take += 1;
-          if (!(k & 1)) level -= 1;  // right child (or root): continue one level up; left child: sibling, same level
-        } else {
-          level += 1;
-        }
+      const uint32_t sh4 = lv4 - cl;                    // 4 + (levels - level)
+      const uint32_t kk  = (kmin | sent) >> sh4;        // 1-based heap index: 2^level + covered / 2^(levels-level)
+      const vec4_t<T> nm = node_m1[kk];
+      const T w          = bw1[kk];
+      // accept: covered += 2^(levels-level); a right child (kk odd; not the root) continues one level up
+      const uint32_t cand_take = kmin + (1u << sh4) - (cl ? (kk & 1u) : 0u);
+      const uint32_t cand_open = kmin + 1u;
+      // (xj - xs) == -(xs - xj) exactly, so one difference serves the reference-order dist2 and the accumulation
+      const T dx = sub_rn(nm.x, xs.x), dy = sub_rn(nm.y, xs.y), dz = D == 3 ? sub_rn(nm.z, xs.z) : T(0);
+      T d2 = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
+      if (D == 3) d2 = add_rn(d2, mul_rn(dz, dz));
+      const bool take = act & (mul_rn(w, w) < mul_rn(theta2, d2));  // can_approximate (bvh.h:246-248)
+      if (take) {
+        T s = nm.w * inv_dist3(d2);
+        ax = fma(dx, s, ax);
+        ay = fma(dy, s, ay);
+        if (D == 3) az = fma(dz, s, az);
       }
+      if (COUNT) n_take += take;
+      key = max(key, take ? cand_take : cand_open);
     }
-    if (act) key = covered >= n ? DONE : ((covered << 5) | level);
   }
   if (COUNT) {
     atomicAdd(&stats[0], n_visit);
@@ -567,9 +574,9 @@ static int force_impl(nbx_engine* e) {
   const T theta = T(e->cfg.theta);
   static const bool per_thread = [] { const char* v = getenv("NBX_BVH_PER_THREAD"); return v && atoi(v); }();
   if (s->levels <= 27 && !per_thread)
-    bvh_force_warp_kernel<T, D><<<(nt + 127) / 128, 128, 0, e->stream>>>(static_cast<const vec4_t<T>*>(e->xm[e->cur]), s->node_m, s->bw,
-                                                                        e->n, e->tb, e->te, s->levels, theta * theta, T(e->cfg.G),
-                                                                        static_cast<vec4_t<T>*>(e->a));
+    bvh_force_key_kernel<T, D><<<(nt + 127) / 128, 128, 0, e->stream>>>(static_cast<const vec4_t<T>*>(e->xm[e->cur]), s->node_m - 1,
+                                                                       s->bw - 1, e->n, e->tb, e->te, s->levels, theta * theta, T(e->cfg.G),
+                                                                       static_cast<vec4_t<T>*>(e->a));
   else
     bvh_force_kernel<T, D><<<(nt + 127) / 128, 128, 0, e->stream>>>(static_cast<const vec4_t<T>*>(e->xm[e->cur]), s->node_m, s->bw, e->n,
                                                                    e->tb, e->te, s->levels, theta * theta, T(e->cfg.G),
@@ -640,8 +647,8 @@ static int stats_impl(nbx_engine* e, unsigned long long* dev_stats) {
   const uint32_t nt = e->te - e->tb;
   const T theta     = T(e->cfg.theta);
   if (nt)
-    bvh_force_warp_kernel<T, D, true><<<(nt + 127) / 128, 128, 0, e->stream>>>(static_cast<const vec4_t<T>*>(e->xm[e->cur]), s->node_m,
-                                                                              s->bw, e->n, e->tb, e->te, s->levels, theta * theta,
+    bvh_force_key_kernel<T, D, true><<<(nt + 127) / 128, 128, 0, e->stream>>>(static_cast<const vec4_t<T>*>(e->xm[e->cur]), s->node_m - 1,
+                                                                              s->bw - 1, e->n, e->tb, e->te, s->levels, theta * theta,
                                                                               T(e->cfg.G), static_cast<vec4_t<T>*>(e->a), dev_stats);
   e->launches++;
   NBX_CUDA(cudaGetLastError());
