@@ -113,37 +113,57 @@ def workload_name(args, n):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# CPU arm: the reference's own implementation (oracle/_ref/nbody_d{2,3}, built from /root/reference/src/main.cpp with its
-# CPU flags minus TBB => serial PSTL backend, 1 core), else the oracle port.
+# CPU arm: the reference's own implementation, the UNMODIFIED /root/reference/src/main.cpp built by oracle/Makefile into
+# oracle/_ref/: nbody_d{2,3}_omp = its CPU flags + an OpenMP PSTL backend (oracle/pstl_backend_omp.h) so that its
+# std::execution::par algorithms use ALL host cores (the image has no TBB, libstdc++'s only parallel backend);
+# nbody_d{2,3}[_native] = the same source with the serial PSTL backend (1 core). Falls back to the oracle port.
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def ref_binary(dim):
-    for name in (f"nbody_d{dim}_native", f"nbody_d{dim}"):
+    """-> (path, threads it runs on) or (None, 0)"""
+    for name, threads in ((f"nbody_d{dim}_omp", host_threads()), (f"nbody_d{dim}_native", 1), (f"nbody_d{dim}", 1)):
         exe = os.path.join(ROOT, "oracle", "_ref", name)
         if os.access(exe, os.X_OK):
             try:  # the -march=native build may not run on this host
                 r = subprocess.run([exe, "-n", "16", "-s", "1", "--workload", "galaxy", "--algorithm", "all-pairs",
                                     "--csv-detailed"], capture_output=True, text=True, timeout=60)
                 if r.returncode == 0:
-                    return exe
+                    return exe, threads
             except (OSError, subprocess.TimeoutExpired):
                 pass
-    return None
+    return None, 0
 
 
-def sample_n(args):
+def ref_descr(exe, threads):
+    if threads > 1:
+        return (f"{os.path.basename(exe)}: unmodified reference, g++ -Ofast -fopenmp, OpenMP PSTL backend "
+                f"(oracle/pstl_backend_omp.h; no TBB in the image), {threads} threads")
+    return f"{os.path.basename(exe)}: unmodified reference, g++ -Ofast, serial PSTL backend (no TBB in the image), 1 thread"
+
+
+def sample_n(args, threads=1):
+    """Bounded sample of the workload: a few seconds of CPU work per step (the metric is a rate, not a wall time)."""
+    par = threads > 1
     if args.algorithm == "all-pairs":
-        return min(args.n, REF_SAMPLE_N)
+        return min(args.n, 100_000 if par else REF_SAMPLE_N)
     if args.algorithm == "all-pairs-collapsed":
-        return min(args.n, 6000)
-    return min(args.n, 200_000)
+        return min(args.n, 20_000 if par else 6000)
+    return min(args.n, 1_000_000 if par else 200_000)
 
 
-def run_reference_once(args, exe, n, steps):
+def run_reference_once(args, exe, n, steps, threads=1):
     """One run of the reference binary, --csv-detailed (exactly `steps` steps, no hidden warm-up: SURVEY §9 Q1).
     Returns seconds for `steps` steps as the reference itself measured them (10 ms resolution) and wall seconds."""
     cmd = [exe, "-n", str(n), "-s", str(steps), "--workload", "galaxy", "--algorithm", args.algorithm,
            "--precision", args.precision, "--theta", str(args.theta), "--csv-detailed"]
+    env = dict(os.environ, OMP_NUM_THREADS=str(max(threads, 1)), OMP_PROC_BIND="false")
     t0 = time.perf_counter()
-    r = subprocess.run(cmd, capture_output=True, text=True, check=True)
+    r = subprocess.run(cmd, capture_output=True, text=True, check=True, env=env)
     wall = time.perf_counter() - t0
     row = [ln for ln in r.stdout.splitlines() if ln.startswith(args.algorithm + ",")][-1].split(",")
     total = float(row[5])
@@ -161,14 +181,13 @@ def cpu_port_rate(args, n, steps):
 
 
 def cpu_baseline(args, steps=1):
-    n = sample_n(args)
-    exe = ref_binary(args.dim)
+    exe, threads = ref_binary(args.dim)
+    n = sample_n(args, threads)
     _, unit = metric_unit(args)
     if exe:
-        secs, _ = run_reference_once(args, exe, n, steps)
-        return {"value": units_per_step(args, n) * steps / secs, "unit": unit, "cores": 1, "kind": "reference",
-                "sample": f"{os.path.basename(exe)} {workload_name(args, n)}, {steps} step(s), --csv-detailed; "
-                          "g++ -Ofast, no TBB in the image => libstdc++ PSTL serial backend (1 core)"}
+        secs, _ = run_reference_once(args, exe, n, steps, threads)
+        return {"value": units_per_step(args, n) * steps / secs, "unit": unit, "cores": threads, "kind": "reference",
+                "sample": f"{workload_name(args, n)}, {steps} step(s), --csv-detailed; {ref_descr(exe, threads)}"}
     rate, cores = cpu_port_rate(args, n, steps)
     return {"value": rate, "unit": unit, "cores": cores, "kind": "port",
             "sample": f"oracle port (-Ofast, OpenMP) {workload_name(args, n)}, {steps} step(s)"}
@@ -179,12 +198,12 @@ def main_reference(args):
     if rank != 0:
         return 0
     metric, unit = metric_unit(args)
-    n = sample_n(args)
-    exe = ref_binary(args.dim)
+    exe, threads = ref_binary(args.dim)
+    n = sample_n(args, threads)
     per_step = []
     for it in range(args.warmup + args.steps):
         if exe:
-            secs, _ = run_reference_once(args, exe, n, 1)
+            secs, _ = run_reference_once(args, exe, n, 1, threads)
         else:
             rate, _ = cpu_port_rate(args, n, 1)
             secs = units_per_step(args, n) / rate
@@ -193,9 +212,9 @@ def main_reference(args):
     total = sum(per_step)
     value = units_per_step(args, n) * args.steps / total
     kind = "reference" if exe else "port"
-    cores = 1 if exe else os.cpu_count()
-    sample = (f"{os.path.basename(exe) if exe else 'oracle port'} {workload_name(args, n)}; each step = one process run "
-              f"of 1 step (--csv-detailed); serial PSTL backend (no TBB in the image)")
+    cores = threads if exe else os.cpu_count()
+    sample = (f"{workload_name(args, n)}; each step = one process run of 1 step (--csv-detailed); "
+              f"{ref_descr(exe, threads) if exe else 'oracle port (-Ofast, OpenMP)'}")
     line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32" if args.precision == "float" else "f64",
@@ -386,12 +405,21 @@ def main_nbx(args):
                 "clocks": clk, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args)
-            try:  # context only: the oracle port (-Ofast, OpenMP) on ALL host cores, same bounded sample
-                rate, cores = cpu_port_rate(args, sample_n(args), 1)
-                line["cpu_port_all_cores"] = {"value": rate, "unit": unit, "cores": cores, "kind": "port",
-                                              "sample": f"oracle port (-Ofast, OpenMP) {workload_name(args, sample_n(args))}, 1 step"}
+            try:  # context only: the same reference source on ONE thread (serial PSTL backend), smaller sample
+                exe1 = next((os.path.join(ROOT, "oracle", "_ref", f"nbody_d{args.dim}{sfx}") for sfx in ("_native", "")
+                             if os.access(os.path.join(ROOT, "oracle", "_ref", f"nbody_d{args.dim}{sfx}"), os.X_OK)), None)
+                if exe1 and line["cpu_baseline"].get("cores", 1) > 1:
+                    n1 = sample_n(args, 1)
+                    try:
+                        secs, _ = run_reference_once(args, exe1, n1, 1, 1)
+                    except (OSError, subprocess.CalledProcessError):  # -march=native built elsewhere
+                        exe1 = os.path.join(ROOT, "oracle", "_ref", f"nbody_d{args.dim}")
+                        secs, _ = run_reference_once(args, exe1, n1, 1, 1)
+                    line["cpu_reference_1thread"] = {"value": units_per_step(args, n1) / secs, "unit": unit, "cores": 1,
+                                                     "kind": "reference",
+                                                     "sample": f"{workload_name(args, n1)}, 1 step; {ref_descr(exe1, 1)}"}
             except Exception as ex:  # noqa: BLE001 - the extra figure must never break the bench line
-                line["cpu_port_all_cores"] = {"error": str(ex)}
+                line["cpu_reference_1thread"] = {"error": str(ex)}
         print(json.dumps(line), flush=True)
     eng.close()
     if dist:
