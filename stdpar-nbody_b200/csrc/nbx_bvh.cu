@@ -59,6 +59,7 @@ struct BvhState {
   uint32_t* perm   = nullptr;
   vec4_t<T>* node_m = nullptr;  // (com.x, com.y, com.z, mass)
   T* bw             = nullptr;
+  T* bw2            = nullptr;  // bw*bw (rounded once, as bvh.h:247 does per test): what the traversal loads
   vec4_t<T>* lo     = nullptr;
   vec4_t<T>* hi     = nullptr;
   bool have_box = false, sorted = false, built = false;
@@ -218,7 +219,7 @@ __device__ __forceinline__ T node_width(vec4_t<T> lo, vec4_t<T> hi) {  // bvh.h:
 // deepest tree level from pairs of bodies (bvh.h:178-207)
 template <typename T, int D>
 __global__ void __launch_bounds__(256) build_leaf_level_kernel(const vec4_t<T>* __restrict__ xm, uint32_t n, uint32_t first,
-                                                               uint32_t count, vec4_t<T>* node_m, T* bw, vec4_t<T>* lo,
+                                                               uint32_t count, vec4_t<T>* node_m, T* bw, T* bw2, vec4_t<T>* lo,
                                                                vec4_t<T>* hi) {
   uint32_t li = blockIdx.x * 256 + threadIdx.x;
   if (li >= count) return;
@@ -234,7 +235,8 @@ __global__ void __launch_bounds__(256) build_leaf_level_kernel(const vec4_t<T>* 
     vec4_t<T> blo = make_v4<T>(sub_rn(pl.x, tol), sub_rn(pl.y, tol), D == 3 ? sub_rn(pl.z, tol) : T(0), 0);
     vec4_t<T> bhi = make_v4<T>(add_rn(pl.x, tol), add_rn(pl.y, tol), D == 3 ? add_rn(pl.z, tol) : T(0), 0);
     lo[i] = blo; hi[i] = bhi;
-    bw[i] = node_width<T, D>(blo, bhi);
+    const T w = node_width<T, D>(blo, bhi);
+    bw[i] = w; bw2[i] = mul_rn(w, w);
     return;
   }
   vec4_t<T> pr = xm[br];
@@ -250,12 +252,13 @@ __global__ void __launch_bounds__(256) build_leaf_level_kernel(const vec4_t<T>* 
   vec4_t<T> bhi = make_v4<T>(add_rn(tmax(pl.x, pr.x), tol), add_rn(tmax(pl.y, pr.y), tol),
                              D == 3 ? add_rn(tmax(pl.z, pr.z), tol) : T(0), 0);
   lo[i] = blo; hi[i] = bhi;
-  bw[i] = node_width<T, D>(blo, bhi);
+  const T w = node_width<T, D>(blo, bhi);
+  bw[i] = w; bw2[i] = mul_rn(w, w);
 }
 
 // one upper level from its children (bvh.h:210-243)
 template <typename T, int D>
-__global__ void __launch_bounds__(256) build_level_kernel(uint32_t first, uint32_t count, vec4_t<T>* node_m, T* bw,
+__global__ void __launch_bounds__(256) build_level_kernel(uint32_t first, uint32_t count, vec4_t<T>* node_m, T* bw, T* bw2,
                                                           vec4_t<T>* lo, vec4_t<T>* hi) {
   uint32_t li = blockIdx.x * 256 + threadIdx.x;
   if (li >= count) return;
@@ -268,7 +271,7 @@ __global__ void __launch_bounds__(256) build_level_kernel(uint32_t first, uint32
   if (!(mr.w != T(0))) {
     node_m[i] = ml;
     lo[i] = lo[bl]; hi[i] = hi[bl];
-    bw[i] = bw[bl];
+    bw[i] = bw[bl]; bw2[i] = bw2[bl];
     return;
   }
   T mass = add_rn(ml.w, mr.w);
@@ -282,7 +285,8 @@ __global__ void __launch_bounds__(256) build_level_kernel(uint32_t first, uint32
   vec4_t<T> blo = make_v4<T>(tmin(l0.x, l1.x), tmin(l0.y, l1.y), D == 3 ? tmin(l0.z, l1.z) : T(0), 0);
   vec4_t<T> bhi = make_v4<T>(tmax(h0.x, h1.x), tmax(h0.y, h1.y), D == 3 ? tmax(h0.z, h1.z) : T(0), 0);
   lo[i] = blo; hi[i] = bhi;
-  bw[i] = node_width<T, D>(blo, bhi);
+  const T w = node_width<T, D>(blo, bhi);
+  bw[i] = w; bw2[i] = mul_rn(w, w);
 }
 
 // ---- K16 traversal ------------------------------------------------------------------------------------------------
@@ -368,17 +372,21 @@ __global__ void __launch_bounds__(128) bvh_force_kernel(const vec4_t<T>* __restr
 // covered >= n, i.e. key >= nlim; the warp stops when the minimum is.
 template <typename T, int D, bool COUNT = false>
 __global__ void __launch_bounds__(128) bvh_force_key_kernel(const vec4_t<T>* __restrict__ xm, const vec4_t<T>* __restrict__ node_m1,
-                                                            const T* __restrict__ bw1, uint32_t n, uint32_t tb, uint32_t te,
+                                                            const T* __restrict__ bw2_1, uint32_t n, uint32_t tb, uint32_t te,
                                                             uint32_t levels, T theta2, T c, vec4_t<T>* __restrict__ a_out,
                                                             unsigned long long* stats = nullptr) {
-  // node_m1 / bw1 are the node arrays offset by -1 element: indexed by the 1-based heap index kk = k + 1
+  // node_m1 / bw2_1 are the node arrays (centre of mass + mass, width^2) offset by -1 element: indexed by the 1-based
+  // heap index kk = k + 1
   const uint32_t i   = tb + blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid   = i < te;
   const vec4_t<T> xs = xm[valid ? i : tb];
   unsigned long long n_visit = 0, n_take = 0, n_step = 0;  // COUNT only
-  const uint32_t nlim = (n + (n & 1u)) << 4;  // covered is even: covered >= n  <=>  covered >= n rounded up to even
-  const uint32_t sent = 16u << levels;        // one above the largest active covered << 4
-  const uint32_t lv4  = levels + 4;
+  // covered is even: covered >= n <=> covered >= n rounded up to even. Active keys are <= ((n_even - 2) << 4) + 27, so the
+  // limit can sit 4 below n_even << 4: accepting the ROOT (a "right child" by parity of kk = 1) then needs no special case,
+  // its candidate (2^levels << 4) - 1 is past the limit for every n <= 2^levels.
+  const uint32_t nlim  = ((n + (n & 1u)) << 4) - 4u;
+  const uint32_t sent  = 16u << levels;  // one above the largest active covered << 4
+  const uint32_t step0 = 16u << levels;  // key increment of accepting a level-0 node; >> level for deeper ones
   uint32_t key = valid ? 0u : 0xffffffffu;
   T ax = 0, ay = 0, az = 0;
   for (;;) {
@@ -408,18 +416,17 @@ __global__ void __launch_bounds__(128) bvh_force_key_kernel(const vec4_t<T>* __r
       if (act) key = kmin + (cl ? 31u : 32u);  // covered += 2, level -= 1 (n = 1: the body level is level 0)
       if (COUNT) n_take += act;
     } else {
-      const uint32_t sh4 = lv4 - cl;                    // 4 + (levels - level)
-      const uint32_t kk  = (kmin | sent) >> sh4;        // 1-based heap index: 2^level + covered / 2^(levels-level)
+      const uint32_t kk  = (kmin | sent) >> (levels + 4u - cl);  // 1-based heap index: 2^level + covered / 2^(levels-level)
       const vec4_t<T> nm = node_m1[kk];
-      const T w          = bw1[kk];
-      // accept: covered += 2^(levels-level); a right child (kk odd; not the root) continues one level up
-      const uint32_t cand_take = kmin + (1u << sh4) - (cl ? (kk & 1u) : 0u);
+      const T w2         = bw2_1[kk];
+      // accept: covered += 2^(levels-level); a right child (kk odd) continues one level up, a left child with its sibling
+      const uint32_t cand_take = kmin + (step0 >> cl) - (kk & 1u);
       const uint32_t cand_open = kmin + 1u;
       // (xj - xs) == -(xs - xj) exactly, so one difference serves the reference-order dist2 and the accumulation
       const T dx = sub_rn(nm.x, xs.x), dy = sub_rn(nm.y, xs.y), dz = D == 3 ? sub_rn(nm.z, xs.z) : T(0);
       T d2 = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
       if (D == 3) d2 = add_rn(d2, mul_rn(dz, dz));
-      const bool take = act & (mul_rn(w, w) < mul_rn(theta2, d2));  // can_approximate (bvh.h:246-248)
+      const bool take = act & (w2 < mul_rn(theta2, d2));  // can_approximate (bvh.h:246-248)
       if (take) {
         T s = nm.w * inv_dist3(d2);
         ax = fma(dx, s, ax);
@@ -483,11 +490,13 @@ static int create_impl(nbx_engine* e) {
   const size_t nn = size_t(s->nnodes ? s->nnodes : 1);
   NBX_CUDA(cudaMalloc(&s->node_m, sizeof(vec4_t<T>) * nn));
   NBX_CUDA(cudaMalloc(&s->bw, sizeof(T) * nn));
+  NBX_CUDA(cudaMalloc(&s->bw2, sizeof(T) * nn));
   NBX_CUDA(cudaMalloc(&s->lo, sizeof(vec4_t<T>) * nn));
   NBX_CUDA(cudaMalloc(&s->hi, sizeof(vec4_t<T>) * nn));
   // the reference never writes b/bw of dead nodes (bvh.h:185-188,225-228): keep them deterministic (zero)
   NBX_CUDA(cudaMemsetAsync(s->node_m, 0, sizeof(vec4_t<T>) * nn, e->stream));
   NBX_CUDA(cudaMemsetAsync(s->bw, 0, sizeof(T) * nn, e->stream));
+  NBX_CUDA(cudaMemsetAsync(s->bw2, 0, sizeof(T) * nn, e->stream));
   NBX_CUDA(cudaMemsetAsync(s->lo, 0, sizeof(vec4_t<T>) * nn, e->stream));
   NBX_CUDA(cudaMemsetAsync(s->hi, 0, sizeof(vec4_t<T>) * nn, e->stream));
   const size_t rb = rec_bytes(e);
@@ -504,7 +513,7 @@ template <typename T, int D>
 static void destroy_impl(nbx_engine* e) {
   auto* s = st<T>(e);
   if (!s) return;
-  void* bufs[] = {s->box, s->partial, s->keys, s->perm, s->node_m, s->bw, s->lo, s->hi};
+  void* bufs[] = {s->box, s->partial, s->keys, s->perm, s->node_m, s->bw, s->bw2, s->lo, s->hi};
   for (void* b : bufs)
     if (b) cudaFree(b);
   delete s;
@@ -552,12 +561,12 @@ static int build_impl(nbx_engine* e) {
   const uint32_t last = s->levels - 1;
   {
     uint32_t first = (1u << last) - 1, count = 1u << last;
-    build_leaf_level_kernel<T, D><<<(count + 255) / 256, 256, 0, e->stream>>>(xm, e->n, first, count, s->node_m, s->bw, s->lo, s->hi);
+    build_leaf_level_kernel<T, D><<<(count + 255) / 256, 256, 0, e->stream>>>(xm, e->n, first, count, s->node_m, s->bw, s->bw2, s->lo, s->hi);
     e->launches++;
   }
   for (int l = int(last) - 1; l >= 0; --l) {
     uint32_t first = (1u << l) - 1, count = 1u << l;
-    build_level_kernel<T, D><<<(count + 255) / 256, 256, 0, e->stream>>>(first, count, s->node_m, s->bw, s->lo, s->hi);
+    build_level_kernel<T, D><<<(count + 255) / 256, 256, 0, e->stream>>>(first, count, s->node_m, s->bw, s->bw2, s->lo, s->hi);
     e->launches++;
   }
   NBX_CUDA(cudaGetLastError());
@@ -575,7 +584,7 @@ static int force_impl(nbx_engine* e) {
   static const bool per_thread = [] { const char* v = getenv("NBX_BVH_PER_THREAD"); return v && atoi(v); }();
   if (s->levels <= 27 && !per_thread)
     bvh_force_key_kernel<T, D><<<(nt + 127) / 128, 128, 0, e->stream>>>(static_cast<const vec4_t<T>*>(e->xm[e->cur]), s->node_m - 1,
-                                                                       s->bw - 1, e->n, e->tb, e->te, s->levels, theta * theta, T(e->cfg.G),
+                                                                       s->bw2 - 1, e->n, e->tb, e->te, s->levels, theta * theta, T(e->cfg.G),
                                                                        static_cast<vec4_t<T>*>(e->a));
   else
     bvh_force_kernel<T, D><<<(nt + 127) / 128, 128, 0, e->stream>>>(static_cast<const vec4_t<T>*>(e->xm[e->cur]), s->node_m, s->bw, e->n,
@@ -648,7 +657,7 @@ static int stats_impl(nbx_engine* e, unsigned long long* dev_stats) {
   const T theta     = T(e->cfg.theta);
   if (nt)
     bvh_force_key_kernel<T, D, true><<<(nt + 127) / 128, 128, 0, e->stream>>>(static_cast<const vec4_t<T>*>(e->xm[e->cur]), s->node_m - 1,
-                                                                              s->bw - 1, e->n, e->tb, e->te, s->levels, theta * theta,
+                                                                              s->bw2 - 1, e->n, e->tb, e->te, s->levels, theta * theta,
                                                                               T(e->cfg.G), static_cast<vec4_t<T>*>(e->a), dev_stats);
   e->launches++;
   NBX_CUDA(cudaGetLastError());
