@@ -77,7 +77,7 @@ struct OctreeState {
   uint32_t* depth_count = nullptr;     // [130] cells per depth -> exclusive offsets [0..128], cursor copy at +...
   uint32_t* depth_cursor = nullptr;    // [129]
   vec4_t<T>* a_sorted = nullptr; // [n_pad] accelerations in sorted-slot order
-  T* thr_table        = nullptr; // [132] acceptance thresholds on d2 per depth (threshold_table_kernel)
+  T* thr_table        = nullptr; // [2][132] acceptance thresholds per depth on d2 / on dx (threshold_table_kernel)
   bool built = false;
 };
 
@@ -436,8 +436,8 @@ __global__ void __launch_bounds__(256) monopole_level_kernel(const uint32_t* __r
 
 // ---- K9 traversal ---------------------------------------------------------------------------------------------------
 // octree.h:227-255: dx = sqrt(dist2)+eps ; accept when leaf or side/dx < theta ; a += m*(xj-x)/dx^3.
-// The test is evaluated as side < theta*dx (dx > 0): it can only differ from the reference's division when side/dx is
-// within one rounding of theta.
+// The test is evaluated as side/theta < dx (dx > 0, side/theta tabulated per depth): it can only differ from the
+// reference's division when side/dx is within a rounding or two of theta.
 // exact halvings of the root side: side(depth) = root_side * 2^-depth
 __device__ __forceinline__ float side_at(float root_side, uint32_t depth) { return root_side * __int_as_float(int(127 - depth) << 23); }
 __device__ __forceinline__ double side_at(double root_side, uint32_t depth) {
@@ -449,16 +449,20 @@ __device__ __forceinline__ double side_at(double root_side, uint32_t depth) {
 // load is a single broadcast sector instead of up to 32 divergent ones), while each lane keeps the reference's per-body
 // semantics exactly: a lane that accepts node p while another lane needs it opened simply sleeps until the walk leaves
 // that subtree (`resume` = the record index where it wakes up). Interaction sets are identical to the per-body walk.
+// `s_table` (threshold_table_kernel) holds side(depth)/theta per depth and -1 in the leaf slot [128], so the whole
+// acceptance test is one shared-memory load and one compare: side/theta < dx.
 template <typename T, int D, bool COUNT = false>
 __global__ void __launch_bounds__(128) octree_force_kernel(const vec4_t<T>* __restrict__ mono, const uint2* __restrict__ meta,
                                                            const Root<T>* __restrict__ root, const uint32_t* __restrict__ cell_base,
-                                                           uint32_t n, uint32_t tb, uint32_t te, T theta, T c,
+                                                           uint32_t n, uint32_t tb, uint32_t te, const T* __restrict__ s_table, T c,
                                                            vec4_t<T>* __restrict__ a_sorted, unsigned long long* stats = nullptr) {
+  __shared__ T tab[132];
+  for (uint32_t d = threadIdx.x; d < 132; d += blockDim.x) tab[d] = s_table[d];
+  __syncthreads();
   unsigned long long n_visit = 0, n_take = 0, n_step = 0;  // COUNT only
   const uint32_t t    = tb + blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid    = t < te;
   const uint32_t nrec = n + root->cells;
-  const T root_side   = root->side;
   const uint32_t tt   = valid ? t : tb;
   const vec4_t<T> xs  = mono[tt + cell_base[tt + 1]];  // own leaf record = own position
   T ax = 0, ay = 0, az = 0;
@@ -467,12 +471,13 @@ __global__ void __launch_bounds__(128) octree_force_kernel(const vec4_t<T>* __re
   while (p < nrec) {
     const vec4_t<T> nm = mono[p];  // warp-uniform address
     const uint2 me     = meta[p];
+    const T s_over_th  = tab[min(me.y, 128u)];
     const T dx_ = nm.x - xs.x, dy_ = nm.y - xs.y, dz_ = D == 3 ? nm.z - xs.z : T(0);
     T d2 = fma(dy_, dy_, sq_plus_tiny(dx_));
     if (D == 3) d2 = fma(dz_, dz_, d2);
     const T dx      = dist_eps_pos(d2);
     const bool act  = p >= resume;
-    const bool take = (me.y & LEAF_FLAG) || (side_at(root_side, me.y & 0xff) < theta * dx);
+    const bool take = s_over_th < dx;
     if (COUNT) { n_visit += act; n_take += act && take; n_step += 1; }
     if (act && take) {
       const T s = nm.w * inv_cube(dx);
@@ -519,19 +524,22 @@ __device__ __forceinline__ double mass_inv_cube(double m, double d2) {
   return fma(w3, c2, w3);
 }
 
-// thr[depth] = (side(depth)/theta - eps)^2 evaluated in double, rounded once to T; -1 (always accepted: d2 >= 0) when
-// side/theta <= eps and for the leaf slot [128]; +inf (never accepted) for theta <= 0.
+// Per-depth acceptance tables, evaluated in double and rounded once to T:
+//   thr_table[d]       = (side(d)/theta - eps)^2     threshold on d2 (octree_force_thr_kernel)
+//   thr_table[132 + d] = side(d)/theta               threshold on dx (octree_force_kernel)
+// -1 (always accepted: d2, dx >= 0) when side/theta <= eps and in the leaf slot [128]; +inf (never accepted) for theta <= 0.
 template <typename T>
 __global__ void threshold_table_kernel(const Root<T>* __restrict__ root, T theta, T* __restrict__ thr_table) {
   const uint32_t d = threadIdx.x;
   if (d >= 132) return;
-  double thr = -1.0;
+  double thr = -1.0, S = -1.0;
   if (d < 128) {
     const double eps = sizeof(T) == 4 ? double(FLT_EPSILON) : DBL_EPSILON;
-    const double S   = theta > T(0) ? double(side_at(root->side, d)) / double(theta) : double(INFINITY);
+    S                = theta > T(0) ? double(side_at(root->side, d)) / double(theta) : double(INFINITY);
     thr              = S > eps ? (S - eps) * (S - eps) : -1.0;
   }
-  thr_table[d] = T(thr);
+  thr_table[d]       = T(thr);
+  thr_table[132 + d] = T(S);
 }
 
 template <typename T, int D, bool COUNT = false>
@@ -640,7 +648,7 @@ static int create_impl(nbx_engine* e) {
   NBX_CUDA(cudaMalloc(&s->cells_by_depth, sizeof(uint32_t) * s->ccap));
   NBX_CUDA(cudaMalloc(&s->depth_count, sizeof(uint32_t) * 130));
   NBX_CUDA(cudaMalloc(&s->depth_cursor, sizeof(uint32_t) * 130));
-  NBX_CUDA(cudaMalloc(&s->thr_table, sizeof(T) * 132));
+  NBX_CUDA(cudaMalloc(&s->thr_table, sizeof(T) * 264));
   NBX_CUDA(cudaMalloc(&s->a_sorted, sizeof(vec4_t<T>) * e->n_pad));
   NBX_CUDA(cudaMemsetAsync(s->a_sorted, 0, sizeof(vec4_t<T>) * e->n_pad, e->stream));
   NBX_TRY(sorter_create(e, e->n));
@@ -748,15 +756,14 @@ static int force_impl(nbx_engine* e) {
     // (26.0 vs 29.8 ms). NBX_OCT_WALK=1|2 forces one of them (experiments).
     static const int forced = [] { const char* v = getenv("NBX_OCT_WALK"); return v ? atoi(v) : 0; }();
     const int walk = forced ? forced : (sizeof(T) == 8 ? 2 : 1);
-    if (walk == 2) {
-      threshold_table_kernel<T><<<1, 160, 0, e->stream>>>(s->root, T(e->cfg.theta), s->thr_table);
+    threshold_table_kernel<T><<<1, 160, 0, e->stream>>>(s->root, T(e->cfg.theta), s->thr_table);
+    if (walk == 2)
       octree_force_thr_kernel<T, D><<<(nt + 127) / 128, 128, 0, e->stream>>>(s->mono, s->meta, s->root, s->cnt, e->n, e->tb, e->te,
                                                                             s->thr_table, T(e->cfg.G), s->a_sorted);
-      e->launches++;
-    } else {
+    else
       octree_force_kernel<T, D><<<(nt + 127) / 128, 128, 0, e->stream>>>(s->mono, s->meta, s->root, s->cnt, e->n, e->tb, e->te,
-                                                                        T(e->cfg.theta), T(e->cfg.G), s->a_sorted);
-    }
+                                                                        s->thr_table + 132, T(e->cfg.G), s->a_sorted);
+    e->launches += 2;
     e->launches++;
   }
   if (e->cfg.world_size > 1) NBX_TRY(comm_allgather(e, s->a_sorted));
@@ -816,15 +823,15 @@ static int stats_impl(nbx_engine* e, unsigned long long* dev_stats) {
   auto* s = st<T>(e);
   if (!s->built) return fail(NBX_ERR_STATE, "no octree build has run yet");
   const uint32_t nt = e->te - e->tb;
-  if (nt && sizeof(T) == 8) {  // the counting twin of the walk force_impl launches
+  if (nt) {  // the counting twin of the walk force_impl launches
     threshold_table_kernel<T><<<1, 160, 0, e->stream>>>(s->root, T(e->cfg.theta), s->thr_table);
-    octree_force_thr_kernel<T, D, true><<<(nt + 127) / 128, 128, 0, e->stream>>>(s->mono, s->meta, s->root, s->cnt, e->n, e->tb, e->te,
-                                                                                s->thr_table, T(e->cfg.G), s->a_sorted, dev_stats);
+    if (sizeof(T) == 8)
+      octree_force_thr_kernel<T, D, true><<<(nt + 127) / 128, 128, 0, e->stream>>>(s->mono, s->meta, s->root, s->cnt, e->n, e->tb, e->te,
+                                                                                  s->thr_table, T(e->cfg.G), s->a_sorted, dev_stats);
+    else
+      octree_force_kernel<T, D, true><<<(nt + 127) / 128, 128, 0, e->stream>>>(s->mono, s->meta, s->root, s->cnt, e->n, e->tb, e->te,
+                                                                              s->thr_table + 132, T(e->cfg.G), s->a_sorted, dev_stats);
     e->launches += 2;
-  } else if (nt) {
-    octree_force_kernel<T, D, true><<<(nt + 127) / 128, 128, 0, e->stream>>>(s->mono, s->meta, s->root, s->cnt, e->n, e->tb, e->te,
-                                                                            T(e->cfg.theta), T(e->cfg.G), s->a_sorted, dev_stats);
-    e->launches++;
   }
   NBX_CUDA(cudaGetLastError());
   return NBX_OK;
