@@ -394,6 +394,8 @@ def main_nbx(args):
             if tr and world == 1:
                 roofline["traffic"] = tr["bytes"]
                 roofline["traffic_source"] = "profiles/" + tr["source"]
+                if roofline.get("kernel_ms"):  # what actually reaches HBM (ncu) over the kernel time measured here
+                    roofline["dram_gbs"] = tr["bytes"] / (roofline["kernel_ms"] * 1e-3) / 1e9
         except (OSError, ValueError):
             pass
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
