@@ -59,11 +59,15 @@ class Oracle:
     # models.h:112-136
     def galaxy(self, n, dtype, dim):
         size = int(2 * (n / 2.0))
-        m = np.zeros(size, dtype)
-        x = np.zeros((size, dim), dtype)
-        v = np.zeros((size, dim), dtype)
+        # the model always places its two centre bodies (models.h:126,132): for n = 1 the reference writes the second one
+        # past its 1-body System; give the restatement room for it and return the System-sized prefix
+        cap = max(size, 2)
+        m = np.zeros(cap, dtype)
+        x = np.zeros((cap, dim), dtype)
+        v = np.zeros((cap, dim), dtype)
         got = self._fn("nbo_galaxy", dtype, dim, C.c_uint32)(C.c_uint32(n), _p(m), _p(x), _p(v))
         assert got == size
+        m, x, v = m[:size].copy(), x[:size].copy(), v[:size].copy()
         return dict(m=m, x=x, v=v, a=np.zeros_like(x), ao=np.zeros_like(x), dt=np.dtype(dtype).type(10.0), G=np.dtype(dtype).type(1e-4))
 
     # all_pairs.h:14-27
@@ -225,6 +229,14 @@ class Oracle:
             visits = f(C.c_uint32(n), ct(G), ct(theta), _p(x), ct(tree["side"]), _p(fc), _p(par), _p(nm),
                        C.c_uint32(len(targets)), _p(targets), _p(a))
         return a, int(visits)
+
+    def octree_visits_nonempty(self, x, tree, theta):
+        """(body, node) tests of the reference walk that hit a NON-EMPTY node (empty children contribute +0)."""
+        n, dim = x.shape
+        _, ct = _suffix(x.dtype, dim)
+        f = self._fn("nbo_octree_visits_nonempty", x.dtype, dim, C.c_uint64)
+        return int(f(C.c_uint32(n), ct(theta), _p(x), ct(tree["side"]), _p(np.ascontiguousarray(tree["first_child"])),
+                     _p(np.ascontiguousarray(tree["parent"])), _p(np.ascontiguousarray(tree["node_m"]))))
 
     def permute(self, perm, s):
         n, dim = s["x"].shape

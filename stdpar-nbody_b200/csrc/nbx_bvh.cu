@@ -556,7 +556,10 @@ static int sort_impl(nbx_engine* e) {
 template <typename T, int D>
 static int build_impl(nbx_engine* e) {
   auto* s = st<T>(e);
-  if (s->levels == 0) return NBX_OK;
+  if (s->levels == 0) {  // n = 1: no tree nodes, the walk only meets the body level (bvh.h:288-303)
+    s->built = true;
+    return NBX_OK;
+  }
   const vec4_t<T>* xm = static_cast<const vec4_t<T>*>(e->xm[e->cur]);
   const uint32_t last = s->levels - 1;
   {

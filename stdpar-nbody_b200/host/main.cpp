@@ -146,6 +146,10 @@ struct HostSystem {
       : size(n), dt(dt_), constant(c_), m(n), x(std::size_t(n) * N), v(std::size_t(n) * N), a(std::size_t(n) * N), ao(std::size_t(n) * N) {}
 
   void add(T mass, const std::array<T, N>& pos, const std::array<T, N>& vel) {
+    if (next >= size) {  // galaxy with n = 1 places its second centre body past the System (UB in the reference): drop it
+      ++next;
+      return;
+    }
     m[next] = mass;
     for (int k = 0; k < N; ++k) {
       x[next * N + k] = pos[k];
