@@ -247,41 +247,63 @@ __global__ void __launch_bounds__(256) collapsed_kernel(CollapsedArgs<T> p) {
 }
 
 // ---- energies (system.h:62-79) --------------------------------------------------------------------------------
+// kinetic = 1/2 sum m v^2 ; gravitational = -1/2 G sum_i sum_{j != i} m_i m_j / (|x_i - x_j| + eps)   (dist, vec.h:243-246).
+// The pair term is symmetric, so only the strictly upper triangle is evaluated: the CTA of target tile b sweeps the source
+// tiles jt >= b (in its own tile only the pairs j > i) and the sum is doubled. Per pair: d2, 1/(sqrt(d2)+eps) from MUFU
+// seeds (nbx_math.cuh), one FMA into a per-tile partial in T; the partials are accumulated in double. CTAs are launched heaviest first.
 template <typename T, int D>
-__global__ void __launch_bounds__(256) energy_kernel(const vec4_t<T>* xm, const vec4_t<T>* v, uint32_t n,
+__global__ void __launch_bounds__(256) energy_kernel(const vec4_t<T>* __restrict__ xm, const vec4_t<T>* __restrict__ v, uint32_t n,
                                                       double* out /* [0]=sum m v^2, [1]=sum_i sum_j!=i mi mj / dist */) {
   using V4 = vec4_t<T>;
   __shared__ V4 tile[256];
   __shared__ double red[2][8];
-  uint32_t i   = blockIdx.x * 256 + threadIdx.x;
-  V4 bi        = xm[i < n ? i : 0];
-  V4 vi        = v[i < n ? i : 0];
+  const uint32_t b = blockIdx.x, tid = threadIdx.x;
+  const uint32_t i = b * 256 + tid;
+  const V4 bi      = xm[i < n ? i : n - 1];
+  const V4 vi      = v[i < n ? i : n - 1];
   double ke    = i < n ? double(bi.w) * (double(vi.x) * vi.x + double(vi.y) * vi.y + double(vi.z) * vi.z) : 0.0;
   double total = 0;
-  for (uint32_t j0 = 0; j0 < n; j0 += 256) {
+  for (uint32_t j0 = b * 256; j0 < n; j0 += 256) {
     __syncthreads();
-    uint32_t j        = j0 + threadIdx.x;
-    tile[threadIdx.x] = j < n ? xm[j] : make_v4<T>(0, 0, 0, 0);
+    const uint32_t j = j0 + tid;
+    tile[tid]        = j < n ? xm[j] : make_v4<T>(0, 0, 0, 0);  // zero mass: contributes exactly 0
     __syncthreads();
-    uint32_t cnt = n - j0 < 256 ? n - j0 : 256;
-    for (uint32_t q = 0; q < cnt; ++q) {
-      V4 b = tile[q];
-      T dx = bi.x - b.x, dy = bi.y - b.y, dz = bi.z - b.z;
-      T d  = sqrt(dx * dx + dy * dy + dz * dz) + (sizeof(T) == 4 ? T(FLT_EPSILON) : T(DBL_EPSILON));  // vec.h:243-246
-      if (j0 + q != i) total += double(bi.w * b.w / d);
+    // four interleaved partial sums in T per tile, then double: a heavy source (a galaxy centre) swamps the small terms
+    // added after it in its own partial only
+    T part[4] = {0, 0, 0, 0};
+    if (j0 == b * 256) {  // own tile: strictly upper triangle
+#pragma unroll 4
+      for (uint32_t q = 0; q < 256; ++q) {
+        const V4 s = tile[q];
+        const T dx = bi.x - s.x, dy = bi.y - s.y, dz = D == 3 ? bi.z - s.z : T(0);
+        T d2 = fma(dy, dy, sq_plus_tiny(dx));
+        if (D == 3) d2 = fma(dz, dz, d2);
+        const T t = s.w * inv_dist_eps(d2);
+        part[q & 3] += q > tid ? t : T(0);
+      }
+    } else {
+#pragma unroll 8
+      for (uint32_t q = 0; q < 256; ++q) {
+        const V4 s = tile[q];
+        const T dx = bi.x - s.x, dy = bi.y - s.y, dz = D == 3 ? bi.z - s.z : T(0);
+        T d2 = fma(dy, dy, sq_plus_tiny(dx));
+        if (D == 3) d2 = fma(dz, dz, d2);
+        part[q & 3] = fma(s.w, inv_dist_eps(d2), part[q & 3]);
+      }
     }
+    total += (double(part[0]) + double(part[1])) + (double(part[2]) + double(part[3]));
   }
-  if (i >= n) total = 0;
+  total = i < n ? 2.0 * double(bi.w) * total : 0.0;
   for (int off = 16; off > 0; off >>= 1) {
     ke += __shfl_xor_sync(0xffffffffu, ke, off);
     total += __shfl_xor_sync(0xffffffffu, total, off);
   }
-  if ((threadIdx.x & 31) == 0) {
-    red[0][threadIdx.x >> 5] = ke;
-    red[1][threadIdx.x >> 5] = total;
+  if ((tid & 31) == 0) {
+    red[0][tid >> 5] = ke;
+    red[1][tid >> 5] = total;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     double k2 = 0, g2 = 0;
     for (int w = 0; w < 8; ++w) { k2 += red[0][w]; g2 += red[1][w]; }
     atomicAdd(&out[0], k2);

@@ -74,6 +74,15 @@ __device__ __forceinline__ double dist_eps_pos(double d2) {
   y              = fma(y, q, y);
   return fma(d2, y, DBL_EPSILON);
 }
+// 1 / (sqrt(d2) + eps) for the energies (vec.h:243-246 dist): MUFU seeds; double refined like the force kernels.
+// (A Newton step on each float seed was measured: 1.5x slower, no change in the summed energy — the float error is in the
+// accumulation, not in the seeds.)
+__device__ __forceinline__ float inv_dist_eps(float d2) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(dist_eps(d2)));
+  return r;
+}
+__device__ __forceinline__ double inv_dist_eps(double d2) { return rcp_fast(dist_eps_pos(d2)); }  // d2 > 0 (sq_plus_tiny)
 __device__ __forceinline__ float inv_cube(float dx) {
   float inv;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(dx * dx * dx));

@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libnbx.so")
+LIB_PATH = os.environ.get("NBX_LIB_PATH") or os.path.join(HERE, "lib", "libnbx.so")
 
 ALL_PAIRS, ALL_PAIRS_COLLAPSED, OCTREE, BVH = 0, 1, 2, 3
 ALGORITHMS = {"all-pairs": ALL_PAIRS, "all-pairs-collapsed": ALL_PAIRS_COLLAPSED, "octree": OCTREE, "bvh": BVH}

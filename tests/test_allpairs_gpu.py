@@ -152,6 +152,26 @@ def test_energies(oracle):
     assert abs(k2 - k) <= 1e-12 * abs(k) and abs(g2 - gpot) <= 1e-12 * abs(gpot)
 
 
+@pytest.mark.parametrize("dt,dim,n,tol", [(np.float64, 2, 1999, 1e-12), (np.float64, 3, 5000, 1e-12),
+                                          (np.float32, 3, 3001, 2e-6), (np.float32, 2, 777, 2e-6)])
+def test_energies_sizes(oracle, dt, dim, n, tol):
+    """calc_energies evaluates the strictly upper triangle and doubles it; compared with the formula in double
+    (the reference accumulates in T: its own float result is only good to ~1e-4 at these sizes)."""
+    s = oracle.galaxy(n, dt, dim)
+    m, x, v = s["m"].astype(np.float64), s["x"].astype(np.float64), s["v"].astype(np.float64)
+    eps = float(np.finfo(dt).eps)
+    k = 0.5 * (m * (v * v).sum(1)).sum()
+    d = np.sqrt(((x[:, None, :] - x[None, :, :]) ** 2).sum(-1)) + eps
+    w = (m[:, None] * m[None, :]) / d
+    np.fill_diagonal(w, 0.0)
+    g = -0.5 * float(s["G"]) * w.sum()
+    with nbx.Engine(len(m), dim, dt, "all-pairs", s["dt"], s["G"]) as e:
+        e.upload_state(s)
+        k2, g2 = e.calc_energies()
+    assert abs(k2 - k) <= max(tol, 1e-7 if dt == np.float32 else 0) * abs(k)
+    assert abs(g2 - g) <= tol * abs(g), (g2, g)
+
+
 def test_full_size_properties_1M(oracle_fast):
     """BASELINE config 2 (all-pairs 3-D float, n = 1M): sampled targets against the oracle, plus the
     size-independent property sum_i m_i a_i = 0 (Newton's third law; every pair term is exactly antisymmetric)."""
