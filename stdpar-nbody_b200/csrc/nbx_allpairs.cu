@@ -547,21 +547,17 @@ static int launch_energies(nbx_engine* e, double* out_dev) {
 }
 
 int calc_energies(nbx_engine* e, double* kinetic, double* grav) {
-  double* out = nullptr;
-  NBX_CUDA(cudaMalloc(&out, 2 * sizeof(double)));
+  if (!e->energy_out) NBX_CUDA(cudaMalloc(&e->energy_out, 2 * sizeof(double)));
+  double* out = e->energy_out;
   NBX_CUDA(cudaMemsetAsync(out, 0, 2 * sizeof(double), e->stream));
   int rc;
   if (e->prec == 4) rc = e->dim == 2 ? launch_energies<float, 2>(e, out) : launch_energies<float, 3>(e, out);
   else rc = e->dim == 2 ? launch_energies<double, 2>(e, out) : launch_energies<double, 3>(e, out);
-  double h[2] = {0, 0};
-  if (rc == NBX_OK) {
-    cudaError_t err = cudaMemcpyAsync(h, out, sizeof(h), cudaMemcpyDeviceToHost, e->stream);
-    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
-    if (err != cudaSuccess) rc = fail(NBX_ERR_CUDA, cudaGetErrorString(err));
-    e->d2h += sizeof(h);
-  }
-  cudaFree(out);
   if (rc != NBX_OK) return rc;
+  double h[2] = {0, 0};
+  NBX_CUDA(cudaMemcpyAsync(h, out, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
+  NBX_CUDA(cudaStreamSynchronize(e->stream));
+  e->d2h += sizeof(h);
   if (kinetic) *kinetic = 0.5 * h[0];               // system.h:64-66
   if (grav) *grav = -0.5 * e->cfg.G * h[1];         // system.h:67-77
   return NBX_OK;

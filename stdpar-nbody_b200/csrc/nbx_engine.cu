@@ -311,7 +311,7 @@ int nbx_destroy(nbx_engine* e) {
   octree_destroy(e);
   sorter_destroy(e);
   all_pairs_sym_destroy(e);
-  void* bufs[] = {e->xm[0], e->xm[1], e->v, e->a, e->ao, e->v_alt, e->a_alt, e->ao_alt, e->partial, e->tickets, e->stage};
+  void* bufs[] = {e->xm[0], e->xm[1], e->v, e->a, e->ao, e->v_alt, e->a_alt, e->ao_alt, e->partial, e->tickets, e->stage, e->energy_out};
   for (void* b : bufs)
     if (b) cudaFree(b);
   for (int k = 0; k < 2; ++k) {

@@ -82,6 +82,7 @@ struct nbx_engine {
   size_t partial_bytes = 0;
   uint32_t* tickets = nullptr; // per i-block arrival counters (self-resetting)
   size_t tickets_count = 0;
+  double* energy_out = nullptr;  // [2] result slot of calc_energies (allocated on first use)
 
   // host<->device staging for upload/download (AoS <-> vec4 conversion happens on the device)
   void* stage = nullptr;
