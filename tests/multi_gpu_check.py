@@ -25,7 +25,10 @@ def main():
     orc = O.Oracle(fast=True)
     ok = True
     for algo, dt, n, dim in (("all-pairs", np.float32, 9001, 3), ("all-pairs", np.float32, 70001, 3), ("all-pairs-collapsed", np.float64, 3001, 3),
-                             ("bvh", np.float32, 50021, 3), ("octree", np.float64, 40009, 3), ("bvh", np.float64, 7001, 2)):
+                             ("bvh", np.float32, 50021, 3), ("octree", np.float64, 40009, 3), ("bvh", np.float64, 7001, 2),
+                             ("octree", np.float32, 30011, 3)):
+        # the last case runs the octree walk with its lanes in Hilbert order (the default only from n = 4 M)
+        os.environ["NBX_OCT_HILBERT"] = "1" if (algo, dt) == ("octree", np.float32) else "0"
         s = orc.galaxy(n, dt, dim)
         n = len(s["m"])
         with nbx.Engine(n, dim, dt, algo, s["dt"], s["G"], device=local, rank=rank, world_size=world) as e:

@@ -128,6 +128,25 @@ def test_deep_tree_two_word_keys(oracle, tag, dim, gap):
     assert rms(err) <= tr and err.max() <= 10 * tm, (rms(err), err.max())
 
 
+@pytest.mark.parametrize("tag,dim", CASES, ids=IDS)
+def test_hilbert_lane_order_is_bit_identical(oracle, monkeypatch, tag, dim):
+    """For n >= 4 M the walk assigns its lanes along a Hilbert curve instead of the path (Z) order. Only the grouping of
+    bodies into warps changes: every body performs the same operations on the same records, so the result is bit-identical
+    (forced on and off here at a small n)."""
+    s = oracle.galaxy(6001, DT[tag], dim)
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("NBX_OCT_HILBERT", flag)
+        with engine(s) as e:
+            e.octree_build()
+            e.octree_compute_force()
+            out[flag] = e.download(("a",))["a"]
+            st = e.traversal_stats()
+        out["visits" + flag] = st["node_visits"]
+    assert same(out["0"], out["1"])
+    assert out["visits0"] == out["visits1"]
+
+
 def test_coincident_bodies_are_reported(oracle):
     """The reference splits forever on coincident bodies (no capacity check, octree.h:146-169); nbx reports it."""
     s = oracle.galaxy(64, np.float32, 3)
