@@ -20,6 +20,7 @@
 #include <cfloat>
 #include <cstdlib>
 
+#include "nbx_hilbert.cuh"
 #include "nbx_internal.cuh"
 #include "nbx_math.cuh"
 
@@ -461,29 +462,7 @@ __global__ void __launch_bounds__(256) walk_order_keys_kernel(const uint64_t* __
 #pragma unroll
     for (int k = 0; k < D; ++k) X[k] |= ((digit >> k) & 1u) << (HB - 1 - l);
   }
-  const uint32_t M = 1u << (HB - 1);
-  for (uint32_t Q = M; Q > 1; Q >>= 1) {
-    const uint32_t P = Q - 1;
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-      if (X[k] & Q) X[0] ^= P;
-      else {
-        const uint32_t t = (X[0] ^ X[k]) & P;
-        X[0] ^= t;
-        X[k] ^= t;
-      }
-    }
-  }
-#pragma unroll
-  for (int k = 1; k < D; ++k) X[k] ^= X[k - 1];
-  uint32_t t = 0;
-  for (uint32_t Q = M; Q > 1; Q >>= 1)
-    if (X[D - 1] & Q) t ^= Q - 1;
-  uint64_t h = 0;
-  for (int j = HB - 1; j >= 0; --j)
-#pragma unroll
-    for (int k = 0; k < D; ++k) h = (h << 1) | (((X[k] ^ t) >> j) & 1u);
-  hkeys[s] = h;
+  hkeys[s] = hilbert_index<D>(X, HB);
 }
 
 // ---- K9 traversal ---------------------------------------------------------------------------------------------------
