@@ -17,6 +17,7 @@
 // Multi-GPU: units are dealt round-robin to the ranks, the per-rank sums are combined with one ncclAllReduce of the
 // accelerations and every rank integrates all bodies (replicated state, no position exchange).
 #include <cfloat>
+#include <cstdlib>
 
 #include "nbx_device.cuh"
 #include "nbx_internal.cuh"
@@ -33,6 +34,8 @@ constexpr int SYM_WARPS  = 8;
 template <typename T>
 struct SymArgs {
   const vec4_t<T>* xm;
+  const float* soa;   // packed float kernel only: [4][soa_stride] = x[], y[], z[], m[] of the same bodies
+  uint64_t soa_stride;
   vec4_t<T>* P;       // [K][slab]
   uint64_t slab;      // K * B (bodies, padded)
   uint32_t B, K;
@@ -48,8 +51,73 @@ __device__ __forceinline__ void unit_to_blocks(uint32_t u, uint32_t& I, uint32_t
   I = u - uint32_t(uint64_t(j) * (j + 1) / 2);
 }
 
-template <typename T, int D, int RI, int MINB>
+// 1 / (d2^1.5 + eps) for a pair of distances: scalar MUFU.SQRT / MUFU.RCP on the halves, the FMA in between packed
+__device__ __forceinline__ float2 inv_dist3_pair(float2 d2) {
+  float2 sq, inv;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq.x) : "f"(d2.x));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq.y) : "f"(d2.y));
+  const float2 den = __ffma2_rn(d2, sq, make_float2(FLT_EPSILON, FLT_EPSILON));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.x) : "f"(den.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.y) : "f"(den.y));
+  return inv;
+}
+
+// transposed butterfly over the warp: v = 3 components of 4 consecutive j bodies (12 values) -> 6 -> 3 per lane, then three
+// plain stages; lanes 0, 8, 16, 24 end up with the warp totals of bodies j0+0..j0+3 (fixed order => deterministic) and
+// store them to the warp's slice dst[4][3]
+template <typename T>
+__device__ __forceinline__ void sym_reduce4(const T (&v)[12], int lane, T* dst4) {
+  T w[6], u[3];
+  const bool hi16 = lane & 16, hi8 = lane & 8;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    const T mine = hi16 ? v[6 + q] : v[q];
+    const T send = hi16 ? v[q] : v[6 + q];
+    w[q] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const T mine = hi8 ? w[3 + q] : w[q];
+    const T send = hi8 ? w[q] : w[3 + q];
+    u[q] = mine + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    u[q] += __shfl_xor_sync(0xffffffffu, u[q], 4);
+    u[q] += __shfl_xor_sync(0xffffffffu, u[q], 2);
+    u[q] += __shfl_xor_sync(0xffffffffu, u[q], 1);
+  }
+  if ((lane & 7) == 0) {
+    const int jsel = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+    T* dst = dst4 + jsel * 3;
+    dst[0] = u[0]; dst[1] = u[1]; dst[2] = u[2];
+  }
+}
+
+// the CTA is the only writer of P[I][j in J]: sum the 8 warps' partials of body `tid` of the tile and accumulate over the
+// sub-blocks of I in order
+template <typename T>
+__device__ __forceinline__ void sym_flush_reactions(const T* racc, vec4_t<T>* dst, int tid, bool accumulate) {
+  T rx = T(0), ry = T(0), rz = T(0);
+#pragma unroll
+  for (int wq = 0; wq < SYM_WARPS; ++wq) {
+    const T* src = racc + (size_t(wq) * SYM_JT + tid) * 3;
+    rx += src[0]; ry += src[1]; rz += src[2];
+  }
+  if (accumulate) {
+    const vec4_t<T> old = ldcg_v4(dst);
+    rx += old.x; ry += old.y; rz += old.z;
+  }
+  stcg_v4(dst, make_v4<T>(rx, ry, rz, T(0)));
+}
+
+// PACKED (float only): the pair arithmetic runs on FP32x2 instructions (FFMA2 / FADD2 / FMUL2), two j bodies per
+// instruction — the same FMA-pipe work in about half the issue slots (tools/sym2_micro.cu: 22.7 instead of 25.0 cycles per
+// 32 unordered pairs per SMSP). The j tile is staged as SoA (x[], y[], z[], m[]: four bulk copies per tile from the SoA
+// copy of the positions) so that a j pair is one LDS.64 per component; the i bodies are held as duplicated pairs.
+template <typename T, int D, int RI, int MINB, bool PACKED = false>
 __global__ void __launch_bounds__(256, MINB) all_pairs_sym_kernel(SymArgs<T> p) {
+  static_assert(!PACKED || sizeof(T) == 4, "packed arithmetic is FP32x2");
   using V4 = vec4_t<T>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   V4* tiles      = reinterpret_cast<V4*>(smem_raw);
@@ -74,7 +142,14 @@ __global__ void __launch_bounds__(256, MINB) all_pairs_sym_kernel(SymArgs<T> p) 
   auto issue = [&](int k) {  // k-th tile of the CTA's (isub, jt) sequence: the J block is re-swept for every sub-block of I
     const int stage = k % SYM_STAGES;
     mbar_expect_tx(&bars[stage], TILE_BYTES);
-    tma_load_1d(tiles + size_t(stage) * SYM_JT, p.xm + size_t(J0) + size_t(k % int(ntile)) * SYM_JT, TILE_BYTES, &bars[stage]);
+    const size_t j = size_t(J0) + size_t(k % int(ntile)) * SYM_JT;
+    if constexpr (PACKED) {
+      float* dst = reinterpret_cast<float*>(tiles + size_t(stage) * SYM_JT);  // [4][SYM_JT] floats in the same 4 KB
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tma_load_1d(dst + c * SYM_JT, p.soa + c * p.soa_stride + j, TILE_BYTES / 4, &bars[stage]);
+    } else {
+      tma_load_1d(tiles + size_t(stage) * SYM_JT, p.xm + j, TILE_BYTES, &bars[stage]);
+    }
   };
   if (tid == 0)
     for (int k = 0; k < SYM_STAGES && k < total; ++k) issue(k);
@@ -85,17 +160,77 @@ __global__ void __launch_bounds__(256, MINB) all_pairs_sym_kernel(SymArgs<T> p) 
   int k = 0;
   for (uint32_t isub = 0; isub < nsub; ++isub) {
     T xi[RI], yi[RI], zi[RI], mi[RI], ax[RI], ay[RI], az[RI];
+    float2 nx2[PACKED ? RI : 1], ny2[PACKED ? RI : 1], nz2[PACKED ? RI : 1], m2[PACKED ? RI : 1];  // (-x_i, -x_i) ... (m_i, m_i)
+    float2 ax2[PACKED ? RI : 1], ay2[PACKED ? RI : 1], az2[PACKED ? RI : 1];                       // even-j / odd-j partial sums
 #pragma unroll
     for (int t = 0; t < RI; ++t) {
       const V4 b = p.xm[I0 + isub * (256 * RI) + t * 256 + tid];
       xi[t] = b.x; yi[t] = b.y; zi[t] = b.z; mi[t] = b.w;
       ax[t] = ay[t] = az[t] = T(0);
+      if constexpr (PACKED) {
+        nx2[t] = make_float2(-b.x, -b.x); ny2[t] = make_float2(-b.y, -b.y); nz2[t] = make_float2(-b.z, -b.z);
+        m2[t]  = make_float2(b.w, b.w);
+        ax2[t] = ay2[t] = az2[t] = make_float2(0.f, 0.f);
+      }
     }
     for (uint32_t jt = 0; jt < ntile; ++jt, ++k) {
       const int stage = k % SYM_STAGES;
       mbar_wait(&bars[stage], (k / SYM_STAGES) & 1);
       const V4* tile = tiles + size_t(stage) * SYM_JT;
-      if (diag) {
+      if constexpr (PACKED) {
+        const float* tx = reinterpret_cast<const float*>(tile);
+        const float *ty = tx + SYM_JT, *tz = tx + 2 * SYM_JT, *tm = tx + 3 * SYM_JT;
+        if (diag) {
+#pragma unroll 2
+          for (int j = 0; j < SYM_JT; j += 2) {
+            const float2 bx = *reinterpret_cast<const float2*>(tx + j), by = *reinterpret_cast<const float2*>(ty + j);
+            const float2 bz = *reinterpret_cast<const float2*>(tz + j), bm = *reinterpret_cast<const float2*>(tm + j);
+#pragma unroll
+            for (int t = 0; t < RI; ++t) {
+              const float2 dx = __fadd2_rn(bx, nx2[t]), dy = __fadd2_rn(by, ny2[t]);
+              float2 d2 = __ffma2_rn(dy, dy, __fmul2_rn(dx, dx));
+              float2 dz = make_float2(0.f, 0.f);
+              if (D == 3) { dz = __fadd2_rn(bz, nz2[t]); d2 = __ffma2_rn(dz, dz, d2); }
+              const float2 s = __fmul2_rn(bm, inv_dist3_pair(d2));
+              ax2[t] = __ffma2_rn(dx, s, ax2[t]);
+              ay2[t] = __ffma2_rn(dy, s, ay2[t]);
+              if (D == 3) az2[t] = __ffma2_rn(dz, s, az2[t]);
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int j0 = 0; j0 < SYM_JT; j0 += 4) {
+            T v[12];
+#pragma unroll
+            for (int pp = 0; pp < 2; ++pp) {
+              const int j = j0 + 2 * pp;
+              const float2 bx = *reinterpret_cast<const float2*>(tx + j), by = *reinterpret_cast<const float2*>(ty + j);
+              const float2 bz = *reinterpret_cast<const float2*>(tz + j), bm = *reinterpret_cast<const float2*>(tm + j);
+              float2 rx = make_float2(0.f, 0.f), ry = rx, rz = rx;  // + sum dx*sj ; the reaction is its negative
+#pragma unroll
+              for (int t = 0; t < RI; ++t) {
+                const float2 dx = __fadd2_rn(bx, nx2[t]), dy = __fadd2_rn(by, ny2[t]);
+                float2 d2 = __ffma2_rn(dy, dy, __fmul2_rn(dx, dx));
+                float2 dz = make_float2(0.f, 0.f);
+                if (D == 3) { dz = __fadd2_rn(bz, nz2[t]); d2 = __ffma2_rn(dz, dz, d2); }
+                const float2 inv = inv_dist3_pair(d2);
+                const float2 si = __fmul2_rn(bm, inv), sj = __fmul2_rn(m2[t], inv);
+                ax2[t] = __ffma2_rn(dx, si, ax2[t]);
+                ay2[t] = __ffma2_rn(dy, si, ay2[t]);
+                if (D == 3) az2[t] = __ffma2_rn(dz, si, az2[t]);
+                rx = __ffma2_rn(dx, sj, rx);
+                ry = __ffma2_rn(dy, sj, ry);
+                if (D == 3) rz = __ffma2_rn(dz, sj, rz);
+              }
+              v[6 * pp + 0] = -rx.x; v[6 * pp + 1] = -ry.x; v[6 * pp + 2] = -rz.x;
+              v[6 * pp + 3] = -rx.y; v[6 * pp + 4] = -ry.y; v[6 * pp + 5] = -rz.y;
+            }
+            sym_reduce4<T>(v, lane, racc + (size_t(warp) * SYM_JT + j0) * 3);
+          }
+          __syncthreads();
+          sym_flush_reactions<T>(racc, Preact + J0 + jt * SYM_JT + tid, tid, isub != 0);
+        }
+      } else if (diag) {
 #pragma unroll 4
         for (int j = 0; j < SYM_JT; ++j) {
           const V4 b = tile[j];
@@ -136,56 +271,19 @@ __global__ void __launch_bounds__(256, MINB) all_pairs_sym_kernel(SymArgs<T> p) 
             }
             v[3 * jj] = rx; v[3 * jj + 1] = ry; v[3 * jj + 2] = rz;
           }
-          // transposed butterfly over the warp: 12 values -> 6 -> 3 per lane, then three plain stages; lanes 0, 8, 16, 24
-          // end up with the warp totals of bodies j0+0, j0+1, j0+2, j0+3 (fixed order => deterministic)
-          T w[6], u[3];
-          const bool hi16 = lane & 16, hi8 = lane & 8;
-#pragma unroll
-          for (int q = 0; q < 6; ++q) {
-            const T mine = hi16 ? v[6 + q] : v[q];
-            const T send = hi16 ? v[q] : v[6 + q];
-            w[q] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
-          }
-#pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            const T mine = hi8 ? w[3 + q] : w[q];
-            const T send = hi8 ? w[q] : w[3 + q];
-            u[q] = mine + __shfl_xor_sync(0xffffffffu, send, 8);
-          }
-#pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            u[q] += __shfl_xor_sync(0xffffffffu, u[q], 4);
-            u[q] += __shfl_xor_sync(0xffffffffu, u[q], 2);
-            u[q] += __shfl_xor_sync(0xffffffffu, u[q], 1);
-          }
-          if ((lane & 7) == 0) {
-            const int jsel = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
-            T* dst = racc + (size_t(warp) * SYM_JT + j0 + jsel) * 3;
-            dst[0] = u[0]; dst[1] = u[1]; dst[2] = u[2];
-          }
+          sym_reduce4<T>(v, lane, racc + (size_t(warp) * SYM_JT + j0) * 3);
         }
         __syncthreads();
-        {  // the CTA is the only writer of P[I][j in J]: accumulate over the sub-blocks of I in order
-          T rx = T(0), ry = T(0), rz = T(0);
-#pragma unroll
-          for (int wq = 0; wq < SYM_WARPS; ++wq) {
-            const T* src = racc + (size_t(wq) * SYM_JT + tid) * 3;
-            rx += src[0]; ry += src[1]; rz += src[2];
-          }
-          V4* dst = Preact + J0 + jt * SYM_JT + tid;
-          if (isub != 0) {
-            const V4 old = ldcg_v4(dst);
-            rx += old.x; ry += old.y; rz += old.z;
-          }
-          stcg_v4(dst, make_v4<T>(rx, ry, rz, T(0)));
-        }
+        sym_flush_reactions<T>(racc, Preact + J0 + jt * SYM_JT + tid, tid, isub != 0);
       }
       __syncthreads();  // tile (and racc) free again
       if (tid == 0 && k + SYM_STAGES < total) issue(k + SYM_STAGES);
     }
 #pragma unroll
-    for (int t = 0; t < RI; ++t)
+    for (int t = 0; t < RI; ++t) {
+      if constexpr (PACKED) { ax[t] = ax2[t].x + ax2[t].y; ay[t] = ay2[t].x + ay2[t].y; az[t] = az2[t].x + az2[t].y; }
       stcg_v4(Paction + I0 + isub * (256 * RI) + t * 256 + tid, make_v4<T>(ax[t], ay[t], az[t], T(0)));
+    }
   }
 }
 
@@ -247,7 +345,18 @@ struct SymState {
   uint64_t slab = 0;
   void* P    = nullptr;
   void* asum = nullptr;
+  float* soa = nullptr;      // packed float kernel: x[], y[], z[], m[] copy of the current positions, refreshed every step
+  uint64_t soa_stride = 0;
 };
+
+// (x, y, z, m) records -> x[], y[], z[], m[]
+__global__ void __launch_bounds__(256) aos_to_soa_kernel(const float4* __restrict__ xm, uint64_t count, uint64_t stride,
+                                                         float* __restrict__ soa) {
+  const uint64_t i = blockIdx.x * 256ull + threadIdx.x;
+  if (i >= count) return;
+  const float4 b = xm[i];
+  soa[i] = b.x; soa[stride + i] = b.y; soa[2 * stride + i] = b.z; soa[3 * stride + i] = b.w;
+}
 
 }  // namespace
 
@@ -256,7 +365,7 @@ uint32_t all_pairs_sym_block(uint32_t n) {  // B = 1024 * ceil(n / 2^18)  =>  K 
   return 1024u * (mult ? mult : 1);
 }
 
-template <typename T, int D, int RI, int MINB>
+template <typename T, int D, int RI, int MINB, bool PACKED = false>
 static int sym_launch(nbx_engine* e, bool fuse, int nc) {
   SymState* s = static_cast<SymState*>(e->sym);
   if (!s) {
@@ -268,7 +377,18 @@ static int sym_launch(nbx_engine* e, bool fuse, int nc) {
     NBX_CUDA(cudaMalloc(&s->P, sizeof(vec4_t<T>) * s->slab * s->K));
     NBX_CUDA(cudaMalloc(&s->asum, sizeof(vec4_t<T>) * e->n_pad));
   }
-  auto kern = all_pairs_sym_kernel<T, D, RI, MINB>;
+  if constexpr (PACKED) {
+    // the tiles of block J cover [J*B, (J+1)*B) <= K*B records; the position buffers are padded to max(n_pad, K*B) + 1024
+    const uint64_t count = s->slab;
+    if (!s->soa) {
+      s->soa_stride = count;
+      NBX_CUDA(cudaMalloc(&s->soa, sizeof(float) * 4 * count));
+    }
+    aos_to_soa_kernel<<<unsigned((count + 255) / 256), 256, 0, e->stream>>>(static_cast<const float4*>(e->xm[e->cur]), count, s->soa_stride,
+                                                                            s->soa);
+    e->launches++;
+  }
+  auto kern = all_pairs_sym_kernel<T, D, RI, MINB, PACKED>;
   const size_t smem = size_t(SYM_STAGES) * SYM_JT * sizeof(vec4_t<T>) + size_t(SYM_WARPS) * SYM_JT * 3 * sizeof(T) + SYM_STAGES * sizeof(uint64_t);
   NBX_TRY(ensure_dynamic_smem(e, kern, smem));
   const uint32_t world = uint32_t(e->cfg.world_size), rank = uint32_t(e->cfg.rank);
@@ -276,6 +396,8 @@ static int sym_launch(nbx_engine* e, bool fuse, int nc) {
   const uint32_t mine  = uint32_t((units > rank ? units - rank + world - 1 : 0) / world);
   SymArgs<T> p;
   p.xm = static_cast<const vec4_t<T>*>(e->xm[e->cur]);
+  p.soa        = s->soa;
+  p.soa_stride = s->soa_stride;
   p.P  = static_cast<vec4_t<T>*>(s->P);
   p.slab = s->slab;
   p.B = s->B;
@@ -315,7 +437,17 @@ bool all_pairs_sym_enabled(const nbx_engine* e) {
 
 // collapsed_nc: 0 = all_pairs_force semantics; 2 / 3 = all_pairs_collapsed_force semantics over that many components
 int all_pairs_sym_force(nbx_engine* e, bool fuse, int collapsed_nc) {
-  if (e->prec == 4) return e->dim == 2 ? sym_launch<float, 2, 4, 2>(e, fuse, collapsed_nc) : sym_launch<float, 3, 4, 2>(e, fuse, collapsed_nc);
+  if (e->prec == 4) {
+    // FP32x2 kernel, 8 targets per thread where the block size allows it (B a multiple of 256*8), else 4. Measured at
+    // n = 1 M: scalar 361 ms, packed x4 321 ms, packed x8 311 ms per step. NBX_SYM_PACKED=0|1|2 forces scalar / x4 / x8.
+    const char* env  = getenv("NBX_SYM_PACKED");
+    const int forced = env ? atoi(env) : -1;
+    const bool can8 = all_pairs_sym_block(e->n) % 2048u == 0;
+    const int packed = forced >= 0 ? (forced == 2 && !can8 ? 1 : forced) : (can8 ? 2 : 1);
+    if (packed == 2) return e->dim == 2 ? sym_launch<float, 2, 8, 2, true>(e, fuse, collapsed_nc) : sym_launch<float, 3, 8, 2, true>(e, fuse, collapsed_nc);
+    if (packed == 1) return e->dim == 2 ? sym_launch<float, 2, 4, 2, true>(e, fuse, collapsed_nc) : sym_launch<float, 3, 4, 2, true>(e, fuse, collapsed_nc);
+    return e->dim == 2 ? sym_launch<float, 2, 4, 2>(e, fuse, collapsed_nc) : sym_launch<float, 3, 4, 2>(e, fuse, collapsed_nc);
+  }
   // double: 4 targets per thread at one CTA per SM measured 7.6 % faster than 2 targets at two CTAs per SM (the
   // shuffle butterfly is amortised over twice as many pairs)
   return e->dim == 2 ? sym_launch<double, 2, 4, 1>(e, fuse, collapsed_nc) : sym_launch<double, 3, 4, 1>(e, fuse, collapsed_nc);
@@ -326,6 +458,7 @@ void all_pairs_sym_destroy(nbx_engine* e) {
   if (!s) return;
   if (s->P) cudaFree(s->P);
   if (s->asum) cudaFree(s->asum);
+  if (s->soa) cudaFree(s->soa);
   delete s;
   e->sym = nullptr;
 }
