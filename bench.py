@@ -373,7 +373,8 @@ def main_nbx(args):
                         "kernel": "all_pairs_sym_kernel" if (n >= 16384 and args.algorithm == "all-pairs") else "all_pairs_kernel", "kernel_ms": ph.get("force"),
                         "note": f"{FLOP_PER_PAIR[dim]:.0f} algorithmic flop per ORDERED pair x n(n-1)/ranks / force time "
                                 "(pair kernel + partial-sum reduction); for n >= 16384 the kernel evaluates each unordered "
-                                "pair once (Newton's third law, src/all_pairs.h:41-42 TODO) and applies it to both bodies; peak = "
+                                "pair once (Newton's third law, src/all_pairs.h:41-42 TODO) and applies it to both bodies, in float with "
+                                "FP32x2 (FFMA2) pair arithmetic; peak = "
                                 f"{'FFMA' if prec == nbx.F32 else 'DFMA'} microbenchmark measured in this run "
                                 "(MEASURED_PEAKS.json has no FP32/FP64 FMA figure)"}
         else:
