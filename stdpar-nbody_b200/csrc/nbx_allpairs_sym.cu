@@ -5,7 +5,8 @@
 // antisymmetric in floating point ((xj-xi) == -(xi-xj), same d2), so evaluating it once and applying it to both bodies
 // changes nothing but the summation order. The pair kernel is bound by instruction dispatch (11 FMA-pipe + 2 MUFU per
 // ordered pair); sharing dx,dy,dz,d2,sqrt,rcp between the two directions costs 15 FMA-pipe + 2 MUFU per
-// UNORDERED pair, i.e. ~1.5x fewer issue cycles per ordered pair.
+// UNORDERED pair, i.e. ~1.5x fewer issue cycles per ordered pair. In float the pair arithmetic additionally runs on
+// packed FP32x2 instructions (two j bodies per FFMA2/FADD2/FMUL2), which halves the issue slots of the FMA-pipe work.
 //
 // Decomposition (deterministic, no atomics): bodies are cut into K blocks of B bodies (K <= 256). A CTA owns one unit
 // (I, J), I <= J: it sweeps the J block through shared memory (TMA bulk copies, 256-body tiles) once per 256*RI-body
