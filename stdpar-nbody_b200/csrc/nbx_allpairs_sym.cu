@@ -65,9 +65,9 @@ __device__ __forceinline__ float2 inv_dist3_pair(float2 d2) {
 
 // transposed butterfly over the warp: v = 3 components of 4 consecutive j bodies (12 values) -> 6 -> 3 per lane, then three
 // plain stages; lanes 0, 8, 16, 24 end up with the warp totals of bodies j0+0..j0+3 (fixed order => deterministic) and
-// store them to the warp's slice dst[4][3]
+// store them to racc[warp][j0 + 0..3][3]
 template <typename T>
-__device__ __forceinline__ void sym_reduce4(const T (&v)[12], int lane, T* dst4) {
+__device__ __forceinline__ void sym_reduce4(const T (&v)[12], int lane, T* racc, int warp, int j0) {
   T w[6], u[3];
   const bool hi16 = lane & 16, hi8 = lane & 8;
 #pragma unroll
@@ -90,7 +90,7 @@ __device__ __forceinline__ void sym_reduce4(const T (&v)[12], int lane, T* dst4)
   }
   if ((lane & 7) == 0) {
     const int jsel = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
-    T* dst = dst4 + jsel * 3;
+    T* dst = racc + (size_t(warp) * SYM_JT + j0 + jsel) * 3;
     dst[0] = u[0]; dst[1] = u[1]; dst[2] = u[2];
   }
 }
@@ -112,13 +112,157 @@ __device__ __forceinline__ void sym_flush_reactions(const T* racc, vec4_t<T>* ds
   stcg_v4(dst, make_v4<T>(rx, ry, rz, T(0)));
 }
 
+// ---- scalar kernel (double; float behind NBX_SYM_PACKED=0) -----------------------------------------------------------------
+template <typename T, int D, int RI, int MINB>
+__global__ void __launch_bounds__(256, MINB) all_pairs_sym_kernel(SymArgs<T> p) {
+  using V4 = vec4_t<T>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  V4* tiles      = reinterpret_cast<V4*>(smem_raw);
+  T* racc        = reinterpret_cast<T*>(smem_raw + size_t(SYM_STAGES) * SYM_JT * sizeof(V4));  // [warp][j][3]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + size_t(SYM_STAGES) * SYM_JT * sizeof(V4) + size_t(SYM_WARPS) * SYM_JT * 3 * sizeof(T));
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t I, J;
+  unit_to_blocks(p.unit_begin + blockIdx.x * p.unit_stride, I, J);
+  const bool diag     = I == J;
+  const uint32_t I0   = I * p.B, J0 = J * p.B;
+  const uint32_t nsub = p.B / (256 * RI), ntile = p.B / SYM_JT;
+  const int total     = int(nsub * ntile);
+  constexpr uint32_t TILE_BYTES = SYM_JT * sizeof(V4);
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < SYM_STAGES; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&](int k) {  // k-th tile of the CTA's (isub, jt) sequence: the J block is re-swept for every sub-block of I
+    const int stage = k % SYM_STAGES;
+    mbar_expect_tx(&bars[stage], TILE_BYTES);
+    tma_load_1d(tiles + size_t(stage) * SYM_JT, p.xm + size_t(J0) + size_t(k % int(ntile)) * SYM_JT, TILE_BYTES, &bars[stage]);
+  };
+  if (tid == 0)
+    for (int k = 0; k < SYM_STAGES && k < total; ++k) issue(k);
+
+  V4* Paction = p.P + uint64_t(J) * p.slab;  // actions on i in I caused by block J
+  V4* Preact  = p.P + uint64_t(I) * p.slab;  // reactions on j in J caused by block I
+
+  int k = 0;
+  for (uint32_t isub = 0; isub < nsub; ++isub) {
+    T xi[RI], yi[RI], zi[RI], mi[RI], ax[RI], ay[RI], az[RI];
+#pragma unroll
+    for (int t = 0; t < RI; ++t) {
+      const V4 b = p.xm[I0 + isub * (256 * RI) + t * 256 + tid];
+      xi[t] = b.x; yi[t] = b.y; zi[t] = b.z; mi[t] = b.w;
+      ax[t] = ay[t] = az[t] = T(0);
+    }
+    for (uint32_t jt = 0; jt < ntile; ++jt, ++k) {
+      const int stage = k % SYM_STAGES;
+      mbar_wait(&bars[stage], (k / SYM_STAGES) & 1);
+      const V4* tile = tiles + size_t(stage) * SYM_JT;
+      if (diag) {
+#pragma unroll 4
+        for (int j = 0; j < SYM_JT; ++j) {
+          const V4 b = tile[j];
+#pragma unroll
+          for (int t = 0; t < RI; ++t) {
+            T dx = b.x - xi[t], dy = b.y - yi[t];
+            T d2 = fma(dy, dy, sq_plus_tiny(dx));
+            T dz = T(0);
+            if (D == 3) { dz = b.z - zi[t]; d2 = fma(dz, dz, d2); }
+            T s   = b.w * inv_dist3_pos(d2);
+            ax[t] = fma(dx, s, ax[t]);
+            ay[t] = fma(dy, s, ay[t]);
+            if (D == 3) az[t] = fma(dz, s, az[t]);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int j0 = 0; j0 < SYM_JT; j0 += 4) {
+          T v[12];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const V4 b = tile[j0 + jj];
+            T rx = T(0), ry = T(0), rz = T(0);
+#pragma unroll
+            for (int t = 0; t < RI; ++t) {
+              T dx = b.x - xi[t], dy = b.y - yi[t];
+              T d2 = fma(dy, dy, sq_plus_tiny(dx));
+              T dz = T(0);
+              if (D == 3) { dz = b.z - zi[t]; d2 = fma(dz, dz, d2); }
+              const T inv = inv_dist3_pos(d2);
+              const T si = b.w * inv, sj = mi[t] * inv;
+              ax[t] = fma(dx, si, ax[t]);
+              ay[t] = fma(dy, si, ay[t]);
+              if (D == 3) az[t] = fma(dz, si, az[t]);
+              rx = fma(-dx, sj, rx);
+              ry = fma(-dy, sj, ry);
+              if (D == 3) rz = fma(-dz, sj, rz);
+            }
+            v[3 * jj] = rx; v[3 * jj + 1] = ry; v[3 * jj + 2] = rz;
+          }
+          // transposed butterfly over the warp: 12 values -> 6 -> 3 per lane, then three plain stages; lanes 0, 8, 16, 24
+          // end up with the warp totals of bodies j0+0, j0+1, j0+2, j0+3 (fixed order => deterministic)
+          T w[6], u[3];
+          const bool hi16 = lane & 16, hi8 = lane & 8;
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+            const T mine = hi16 ? v[6 + q] : v[q];
+            const T send = hi16 ? v[q] : v[6 + q];
+            w[q] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
+          }
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const T mine = hi8 ? w[3 + q] : w[q];
+            const T send = hi8 ? w[q] : w[3 + q];
+            u[q] = mine + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            u[q] += __shfl_xor_sync(0xffffffffu, u[q], 4);
+            u[q] += __shfl_xor_sync(0xffffffffu, u[q], 2);
+            u[q] += __shfl_xor_sync(0xffffffffu, u[q], 1);
+          }
+          if ((lane & 7) == 0) {
+            const int jsel = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+            T* dst = racc + (size_t(warp) * SYM_JT + j0 + jsel) * 3;
+            dst[0] = u[0]; dst[1] = u[1]; dst[2] = u[2];
+          }
+        }
+        __syncthreads();
+        {  // the CTA is the only writer of P[I][j in J]: accumulate over the sub-blocks of I in order
+          T rx = T(0), ry = T(0), rz = T(0);
+#pragma unroll
+          for (int wq = 0; wq < SYM_WARPS; ++wq) {
+            const T* src = racc + (size_t(wq) * SYM_JT + tid) * 3;
+            rx += src[0]; ry += src[1]; rz += src[2];
+          }
+          V4* dst = Preact + J0 + jt * SYM_JT + tid;
+          if (isub != 0) {
+            const V4 old = ldcg_v4(dst);
+            rx += old.x; ry += old.y; rz += old.z;
+          }
+          stcg_v4(dst, make_v4<T>(rx, ry, rz, T(0)));
+        }
+      }
+      __syncthreads();  // tile (and racc) free again
+      if (tid == 0 && k + SYM_STAGES < total) issue(k + SYM_STAGES);
+    }
+#pragma unroll
+    for (int t = 0; t < RI; ++t)
+      stcg_v4(Paction + I0 + isub * (256 * RI) + t * 256 + tid, make_v4<T>(ax[t], ay[t], az[t], T(0)));
+  }
+}
+
+// ---- FP32x2 kernel --------------------------------------------------------------------------------------------------
 // PACKED (float only): the pair arithmetic runs on FP32x2 instructions (FFMA2 / FADD2 / FMUL2), two j bodies per
 // instruction — the same FMA-pipe work in about half the issue slots (tools/sym2_micro.cu: 22.7 instead of 25.0 cycles per
 // 32 unordered pairs per SMSP). The j tile is staged as SoA (x[], y[], z[], m[]: four bulk copies per tile from the SoA
 // copy of the positions) so that a j pair is one LDS.64 per component; the i bodies are held as duplicated pairs.
-template <typename T, int D, int RI, int MINB, bool PACKED = false>
-__global__ void __launch_bounds__(256, MINB) all_pairs_sym_kernel(SymArgs<T> p) {
-  static_assert(!PACKED || sizeof(T) == 4, "packed arithmetic is FP32x2");
+template <int D, int RI, int MINB>
+__global__ void __launch_bounds__(256, MINB) all_pairs_sym_packed_kernel(SymArgs<float> p) {
+  using T               = float;
+  constexpr bool PACKED = true;
   using V4 = vec4_t<T>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   V4* tiles      = reinterpret_cast<V4*>(smem_raw);
@@ -226,7 +370,7 @@ __global__ void __launch_bounds__(256, MINB) all_pairs_sym_kernel(SymArgs<T> p) 
               v[6 * pp + 0] = -rx.x; v[6 * pp + 1] = -ry.x; v[6 * pp + 2] = -rz.x;
               v[6 * pp + 3] = -rx.y; v[6 * pp + 4] = -ry.y; v[6 * pp + 5] = -rz.y;
             }
-            sym_reduce4<T>(v, lane, racc + (size_t(warp) * SYM_JT + j0) * 3);
+            sym_reduce4<T>(v, lane, racc, warp, j0);
           }
           __syncthreads();
           sym_flush_reactions<T>(racc, Preact + J0 + jt * SYM_JT + tid, tid, isub != 0);
@@ -272,7 +416,7 @@ __global__ void __launch_bounds__(256, MINB) all_pairs_sym_kernel(SymArgs<T> p) 
             }
             v[3 * jj] = rx; v[3 * jj + 1] = ry; v[3 * jj + 2] = rz;
           }
-          sym_reduce4<T>(v, lane, racc + (size_t(warp) * SYM_JT + j0) * 3);
+          sym_reduce4<T>(v, lane, racc, warp, j0);
         }
         __syncthreads();
         sym_flush_reactions<T>(racc, Preact + J0 + jt * SYM_JT + tid, tid, isub != 0);
@@ -389,7 +533,10 @@ static int sym_launch(nbx_engine* e, bool fuse, int nc) {
                                                                             s->soa);
     e->launches++;
   }
-  auto kern = all_pairs_sym_kernel<T, D, RI, MINB, PACKED>;
+  auto kern = [] {
+    if constexpr (PACKED) return all_pairs_sym_packed_kernel<D, RI, MINB>;
+    else return all_pairs_sym_kernel<T, D, RI, MINB>;
+  }();
   const size_t smem = size_t(SYM_STAGES) * SYM_JT * sizeof(vec4_t<T>) + size_t(SYM_WARPS) * SYM_JT * 3 * sizeof(T) + SYM_STAGES * sizeof(uint64_t);
   NBX_TRY(ensure_dynamic_smem(e, kern, smem));
   const uint32_t world = uint32_t(e->cfg.world_size), rank = uint32_t(e->cfg.rank);
