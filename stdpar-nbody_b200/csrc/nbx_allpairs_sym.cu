@@ -505,9 +505,16 @@ __global__ void __launch_bounds__(256) aos_to_soa_kernel(const float4* __restric
 
 }  // namespace
 
-uint32_t all_pairs_sym_block(uint32_t n) {  // B = 1024 * ceil(n / 2^18)  =>  K = ceil(n / B) <= 256
-  uint32_t mult = (n + (1u << 18) - 1) >> 18;
-  return 1024u * (mult ? mult : 1);
+// B: 1024 below n = 2^17 (K = ceil(n / B) <= 128: enough (I, J) units for 148 SMs from n = 16384 on), above that
+// 2048 * ceil(n / 2^19), a multiple of 256 * 8 so that the kernels with 8 targets per thread apply; K <= 256 up to n = 2^27.
+// NBX_SYM_BLOCK1024=1 restores the former rule 1024 * ceil(n / 2^18) (experiments).
+uint32_t all_pairs_sym_block(uint32_t n) {
+  static const bool old_rule = [] { const char* v = getenv("NBX_SYM_BLOCK1024"); return v && atoi(v); }();
+  if (n < (1u << 17) || old_rule) {
+    const uint32_t mult = (n + (1u << 18) - 1) >> 18;
+    return 1024u * (mult ? mult : 1);
+  }
+  return 2048u * ((n + (1u << 19) - 1) >> 19);
 }
 
 template <typename T, int D, int RI, int MINB, bool PACKED = false>
@@ -597,7 +604,14 @@ int all_pairs_sym_force(nbx_engine* e, bool fuse, int collapsed_nc) {
     return e->dim == 2 ? sym_launch<float, 2, 4, 2>(e, fuse, collapsed_nc) : sym_launch<float, 3, 4, 2>(e, fuse, collapsed_nc);
   }
   // double: 4 targets per thread at one CTA per SM measured 7.6 % faster than 2 targets at two CTAs per SM (the
-  // shuffle butterfly is amortised over twice as many pairs)
+  // shuffle butterfly is amortised over twice as many pairs), 8 targets another 4 %
+  {
+    // 8 targets per thread where B allows it: the butterfly and the tile flush are amortised over twice as many pairs
+    // (n = 262144: 59.4 -> 56.9 ms per step, FP64-pipe fraction 0.68 -> 0.71). NBX_SYM_DOUBLE_RI=4 forces 4 (experiments).
+    const char* env = getenv("NBX_SYM_DOUBLE_RI");
+    if (!(env && atoi(env) == 4) && all_pairs_sym_block(e->n) % 2048u == 0)
+      return e->dim == 2 ? sym_launch<double, 2, 8, 1>(e, fuse, collapsed_nc) : sym_launch<double, 3, 8, 1>(e, fuse, collapsed_nc);
+  }
   return e->dim == 2 ? sym_launch<double, 2, 4, 1>(e, fuse, collapsed_nc) : sym_launch<double, 3, 4, 1>(e, fuse, collapsed_nc);
 }
 
