@@ -17,6 +17,7 @@
 //
 // Empty children are not stored: in the reference they contribute m=0 at x=0, i.e. exactly +0 to every sum.
 // Record = monopole (x,y,z,m) + {next, depth|leaf<<8}: 24 B (float) / 40 B (double), read strictly front to back.
+#include <algorithm>
 #include <cfloat>
 #include <cstdlib>
 
@@ -746,7 +747,7 @@ static int build_impl(nbx_engine* e) {
     }
     if (s->hilbert_targets) {  // lane order of the walk (see walk_order_keys_kernel)
       static const int hb_env = [] { const char* v = getenv("NBX_OCT_HB"); return v ? atoi(v) : 0; }();
-      const int hb = hb_env > 0 ? hb_env : (D == 3 ? 10 : 16);
+      const int hb = std::min(hb_env > 0 ? hb_env : (D == 3 ? 10 : 16), D == 3 ? 21 : 32);  // <= MAXL levels, <= 64 key bits
       walk_order_keys_kernel<D><<<gb, 256, 0, e->stream>>>(s->skeys, n, hb, s->hkeys);
       e->launches++;
       NBX_TRY(sort_pairs(e, s->hkeys, n, hb * D, s->order, nullptr));
