@@ -44,8 +44,12 @@ struct AllPairsArgs {
   LeapArgs<T> leap;      // leap.a is also the destination of the acceleration
 };
 
-template <typename T, int D, int TI, int BLOCK, int TILE, int STAGES, int MINB>
+// PACKED (float, TI even): the pair arithmetic of TWO targets per FP32x2 instruction (FFMA2/FADD2/FMUL2), the j body
+// duplicated into both halves. Per target the operations and their order are those of the scalar loop, so the result is
+// bit-identical; only the issue slots of the FMA-pipe work halve.
+template <typename T, int D, int TI, int BLOCK, int TILE, int STAGES, int MINB, bool PACKED = false>
 __global__ void __launch_bounds__(BLOCK, MINB) all_pairs_kernel(AllPairsArgs<T> p) {
+  static_assert(!PACKED || (sizeof(T) == 4 && TI % 2 == 0), "packed arithmetic is FP32x2 over pairs of targets");
   using V4 = vec4_t<T>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   V4* tiles      = reinterpret_cast<V4*>(smem_raw);
@@ -87,6 +91,44 @@ __global__ void __launch_bounds__(BLOCK, MINB) all_pairs_kernel(AllPairsArgs<T> 
     const int stage = k % STAGES;
     mbar_wait(&bars[stage], (k / STAGES) & 1);
     const V4* tile = tiles + size_t(stage) * TILE;
+    if constexpr (PACKED) {
+      constexpr int TP = TI / 2;
+      float2 nx2[TP], ny2[TP], nz2[TP], ax2[TP], ay2[TP], az2[TP];
+#pragma unroll
+      for (int q = 0; q < TP; ++q) {
+        nx2[q] = make_float2(-xi[2 * q], -xi[2 * q + 1]); ny2[q] = make_float2(-yi[2 * q], -yi[2 * q + 1]);
+        nz2[q] = make_float2(-zi[2 * q], -zi[2 * q + 1]);
+        ax2[q] = make_float2(ax[2 * q], ax[2 * q + 1]); ay2[q] = make_float2(ay[2 * q], ay[2 * q + 1]);
+        az2[q] = make_float2(az[2 * q], az[2 * q + 1]);
+      }
+#pragma unroll 4
+      for (int j = 0; j < TILE; ++j) {
+        const V4 b = tile[j];
+        const float2 bx = make_float2(b.x, b.x), by = make_float2(b.y, b.y), bz = make_float2(b.z, b.z), bm = make_float2(b.w, b.w);
+#pragma unroll
+        for (int q = 0; q < TP; ++q) {
+          const float2 dx = __fadd2_rn(bx, nx2[q]), dy = __fadd2_rn(by, ny2[q]);
+          float2 d2 = __ffma2_rn(dy, dy, __fmul2_rn(dx, dx));
+          float2 dz = make_float2(0.f, 0.f);
+          if (D == 3) { dz = __fadd2_rn(bz, nz2[q]); d2 = __ffma2_rn(dz, dz, d2); }
+          float2 sq, inv;
+          asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq.x) : "f"(d2.x));
+          asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq.y) : "f"(d2.y));
+          const float2 den = __ffma2_rn(d2, sq, make_float2(FLT_EPSILON, FLT_EPSILON));
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.x) : "f"(den.x));
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.y) : "f"(den.y));
+          const float2 sm = __fmul2_rn(bm, inv);
+          ax2[q] = __ffma2_rn(dx, sm, ax2[q]);
+          ay2[q] = __ffma2_rn(dy, sm, ay2[q]);
+          if (D == 3) az2[q] = __ffma2_rn(dz, sm, az2[q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < TP; ++q) {
+        ax[2 * q] = ax2[q].x; ax[2 * q + 1] = ax2[q].y; ay[2 * q] = ay2[q].x; ay[2 * q + 1] = ay2[q].y;
+        az[2 * q] = az2[q].x; az[2 * q + 1] = az2[q].y;
+      }
+    } else
 #pragma unroll 4
     for (int j = 0; j < TILE; ++j) {
       const V4 b = tile[j];  // broadcast LDS.128 (2x for double)
@@ -375,9 +417,9 @@ static LeapArgs<T> make_leap(nbx_engine* e, bool to_next) {
 constexpr int AP_STAGES = 4;  // TILE (bodies per shared-memory tile) is 512, or 128 for small n (more CTAs); the position
                               // buffers carry >= 1024 zero-mass padding records, so whole tiles can always be loaded
 
-template <typename T, int D, int TI, int BLOCK, int MINB, int AP_TILE>
+template <typename T, int D, int TI, int BLOCK, int MINB, int AP_TILE, bool PACKED = false>
 static int launch_all_pairs_cfg(nbx_engine* e, bool fuse, uint32_t nsplit, uint32_t tiles_per_split) {
-  auto kern = all_pairs_kernel<T, D, TI, BLOCK, AP_TILE, AP_STAGES, MINB>;
+  auto kern = all_pairs_kernel<T, D, TI, BLOCK, AP_TILE, AP_STAGES, MINB, PACKED>;
   const size_t smem = size_t(AP_STAGES) * AP_TILE * sizeof(vec4_t<T>) + AP_STAGES * sizeof(uint64_t);
   NBX_TRY(ensure_dynamic_smem(e, kern, smem));
   const uint32_t nt      = e->te - e->tb;
@@ -428,6 +470,10 @@ static int launch_all_pairs(nbx_engine* e, bool fuse) {
   int ti               = TI_MAX;
   const uint32_t want  = uint32_t(e->sm_count) * 4;
   while (ti > 1 && ((nt + 256 * ti - 1) / (256 * ti)) * tiles_total < want * 4) ti >>= 1;
+  if (const char* f = getenv("NBX_AP_TI")) {  // experiments: force the target blocking
+    const int v = atoi(f);
+    if (v == 1 || v == 2 || (v == 4 && TI_MAX >= 4)) ti = v;
+  }
   const int block        = 256;
   const uint32_t iblocks = (nt + block * ti - 1) / (block * ti);
   // j-split: aim for >= 32 waves of CTAs (3 resident per SM) while keeping >= 4 tiles per CTA
@@ -439,6 +485,11 @@ static int launch_all_pairs(nbx_engine* e, bool fuse) {
   uint32_t tps = (tiles_total + nsplit - 1) / nsplit;
   nsplit       = (tiles_total + tps - 1) / tps;
   if constexpr (sizeof(T) == 4) {
+    const char* pk = getenv("NBX_AP_PACKED");  // experiments: FP32x2 arithmetic over pairs of targets (bit-identical results)
+    if (pk && atoi(pk)) {
+      if (ti == 4) return launch_all_pairs_cfg<T, D, 4, 256, 3, AP_TILE, true>(e, fuse, nsplit, tps);
+      if (ti == 2) return launch_all_pairs_cfg<T, D, 2, 256, 3, AP_TILE, true>(e, fuse, nsplit, tps);
+    }
     if (ti == 4) return launch_all_pairs_cfg<T, D, 4, 256, 3, AP_TILE>(e, fuse, nsplit, tps);
     if (ti == 2) return launch_all_pairs_cfg<T, D, 2, 256, 3, AP_TILE>(e, fuse, nsplit, tps);
     return launch_all_pairs_cfg<T, D, 1, 256, 3, AP_TILE>(e, fuse, nsplit, tps);
