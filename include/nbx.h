@@ -54,8 +54,10 @@ typedef struct nbx_config {
   double   dt;           /* System::dt   (src/system.h:16)                                                */
   double   G;            /* System::constant (src/system.h:17)                                            */
   double   theta;        /* --theta (src/arguments.h:31)                                                  */
-  /* multi-GPU: this engine computes forces for / integrates targets [rank*ceil(n/world), ...) and all-gathers
-   * positions each step; world_size 1 = single GPU. */
+  /* multi-GPU (world_size > 1, one engine per GPU): the state_t is REPLICATED on every rank; the force work of a step
+   * is sharded (targets [rank*ceil(n/world), ...) for the ordered all-pairs / collapsed / tree walks, block-pair units
+   * dealt round-robin for the symmetric all-pairs kernel), the accelerations are exchanged with one NCCL all-gather /
+   * all-reduce per step and every rank integrates all bodies. world_size 1 = single GPU. */
   int32_t  rank;
   int32_t  world_size;
   uint32_t flags;        /* NBX_FLAG_* */

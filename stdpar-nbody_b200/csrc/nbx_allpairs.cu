@@ -516,6 +516,11 @@ int all_pairs_force(nbx_engine* e, bool fuse_integrate) {
     else rc = small ? launch_all_pairs<double, 3, 128>(e, fuse_integrate) : launch_all_pairs<double, 3, 512>(e, fuse_integrate);
   }
   if (rc == NBX_OK && fuse_integrate) e->cur ^= 1;
+  // multi-GPU, ordered kernel: every rank computed a[tb, te) — gather the shards so that `a` is complete everywhere
+  if (rc == NBX_OK && e->cfg.world_size > 1) {
+    if (fuse_integrate) return fail(NBX_ERR_STATE, "ordered all-pairs on several GPUs integrates after the all-gather of a");
+    rc = comm_allgather(e, e->a);
+  }
   return rc;
 }
 
@@ -560,8 +565,12 @@ int all_pairs_collapsed_force(nbx_engine* e) {
     const int nc = (e->cfg.flags & NBX_FLAG_COLLAPSED_FIX_Z) && e->dim == 3 ? 3 : 2;
     return all_pairs_sym_force(e, false, nc);
   }
-  if (e->prec == 4) return e->dim == 2 ? launch_collapsed<float, 2>(e) : launch_collapsed<float, 3>(e);
-  return e->dim == 2 ? launch_collapsed<double, 2>(e) : launch_collapsed<double, 3>(e);
+  int rc;
+  if (e->prec == 4) rc = e->dim == 2 ? launch_collapsed<float, 2>(e) : launch_collapsed<float, 3>(e);
+  else rc = e->dim == 2 ? launch_collapsed<double, 2>(e) : launch_collapsed<double, 3>(e);
+  // multi-GPU: every rank updated a[tb, te) (reset + relaxed adds) — gather the shards, `a` is complete everywhere
+  if (rc == NBX_OK && e->cfg.world_size > 1) rc = comm_allgather(e, e->a);
+  return rc;
 }
 
 template <typename T, int D>
@@ -580,13 +589,10 @@ int accelerate_range(nbx_engine* e, uint32_t tb, uint32_t te) {
   return e->dim == 2 ? launch_accelerate<double, 2>(e, tb, te) : launch_accelerate<double, 3>(e, tb, te);
 }
 
-// Trees and the symmetric all-pairs keep the whole state replicated on every rank (accelerations are all-gathered /
-// all-reduced), so they integrate all bodies; the ordered all-pairs variants integrate their own targets and all-gather
-// the new positions.
-int accelerate_step(nbx_engine* e) {
-  const bool replicated = e->algo == NBX_BVH || e->algo == NBX_OCTREE || all_pairs_sym_enabled(e);
-  return replicated ? accelerate_range(e, 0, e->n) : accelerate_range(e, e->tb, e->te);
-}
+// The whole state_t is replicated on every rank for every algorithm: the force functions leave the complete
+// acceleration array everywhere (all-gather of the target shards, or all-reduce of the symmetric kernel's per-rank sums),
+// so every rank integrates all bodies and v, a, ao never go stale outside a rank's shard.
+int accelerate_step(nbx_engine* e) { return accelerate_range(e, 0, e->n); }
 
 template <typename T, int D>
 static int launch_energies(nbx_engine* e, double* out_dev) {

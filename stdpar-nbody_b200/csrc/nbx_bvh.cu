@@ -689,8 +689,12 @@ int bvh_build_tree(nbx_engine* e) {
   return BVH_DISPATCH(e, build_impl, e);
 }
 int bvh_compute_force(nbx_engine* e) {
-  PhaseTimer pt(e, PH_TRAVERSE);
-  return BVH_DISPATCH(e, force_impl, e);
+  {
+    PhaseTimer pt(e, PH_TRAVERSE);
+    NBX_TRY(BVH_DISPATCH(e, force_impl, e));
+  }
+  // multi-GPU: a[tb, te) of every rank -> the full acceleration array everywhere (replicated state)
+  return e->cfg.world_size > 1 ? comm_allgather(e, e->a) : NBX_OK;
 }
 int bvh_stats(nbx_engine* e, unsigned long long* dev_stats) { return BVH_DISPATCH(e, stats_impl, e, dev_stats); }
 int bvh_get_bbox(nbx_engine* e, void* xmin, void* xmax) { return BVH_DISPATCH(e, get_bbox_impl, e, xmin, xmax); }

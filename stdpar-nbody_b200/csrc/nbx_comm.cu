@@ -1,11 +1,15 @@
-// nbx_comm.cu — multi-GPU exchange of positions (one process per GPU, NCCL over NVLink 5 / NVSwitch).
+// nbx_comm.cu — multi-GPU exchange of accelerations (one process per GPU, NCCL over NVLink 5 / NVSwitch).
 //
-// The reference has no distributed code; this is new work: targets are sharded by rank
-// (rank r owns [r*chunk, (r+1)*chunk)), every rank keeps all sources, and after each step the new positions of
-// the local shard are all-gathered IN PLACE into the (x,y,z,m) buffer. NCCL is loaded with dlopen so that the
-// single-GPU library has no link-time dependency (inside a torch process this resolves to torch's bundled
-// libnccl.so.2, in the C++ driver to the system one).
+// The reference has no distributed code; this is new work. Every rank keeps the whole state_t (replicated);
+// the FORCE work is sharded and the accelerations are exchanged each step:
+//   * ordered all-pairs / collapsed / bvh / octree: targets sharded by rank (rank r owns [r*chunk, (r+1)*chunk)), the
+//     shards of `a` are all-gathered IN PLACE, then every rank integrates all bodies;
+//   * symmetric all-pairs: (I, J) block-pair units dealt round-robin, per-rank sums combined with one all-reduce.
+// NCCL is loaded with dlopen so that the single-GPU library has no link-time dependency (inside a torch process this
+// resolves to torch's bundled libnccl.so.2, in the C++ driver to the system one).
 #include <dlfcn.h>
+
+#include <mutex>
 
 #include "nbx_internal.cuh"
 
@@ -28,17 +32,13 @@ struct NcclApi {
   bool ok = false;
 };
 
-NcclApi& api() {
-  static NcclApi a;
-  static bool tried = false;
-  if (tried) return a;
-  tried = true;
+static void load_api(NcclApi& a) {
   const char* names[] = {"libnccl.so.2", "libnccl.so"};
   for (const char* nm : names) {
     a.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
     if (a.lib) break;
   }
-  if (!a.lib) return a;
+  if (!a.lib) return;
   a.GetUniqueId    = (decltype(a.GetUniqueId))dlsym(a.lib, "ncclGetUniqueId");
   a.CommInitRank   = (decltype(a.CommInitRank))dlsym(a.lib, "ncclCommInitRank");
   a.CommDestroy    = (decltype(a.CommDestroy))dlsym(a.lib, "ncclCommDestroy");
@@ -46,6 +46,13 @@ NcclApi& api() {
   a.AllReduce      = (decltype(a.AllReduce))dlsym(a.lib, "ncclAllReduce");
   a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.lib, "ncclGetErrorString");
   a.ok             = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.AllReduce && a.GetErrorString;
+}
+
+// the C++ driver calls in from one host thread per GPU: the table is filled exactly once, before anyone reads it
+NcclApi& api() {
+  static NcclApi a;
+  static std::once_flag once;
+  std::call_once(once, load_api, std::ref(a));
   return a;
 }
 
@@ -76,8 +83,6 @@ int comm_init_rank(nbx_engine* e, const void* id128) {
   e->comm = c;
   return NBX_OK;
 }
-
-int comm_allgather_positions(nbx_engine* e) { return comm_allgather(e, e->xm[e->cur]); }
 
 // in-place all-gather of one vec4 array: rank r contributes records [r*chunk, (r+1)*chunk)
 int comm_allgather(nbx_engine* e, void* vec4_array) {

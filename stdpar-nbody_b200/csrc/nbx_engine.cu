@@ -177,21 +177,23 @@ static int one_step(nbx_engine* e) {
   const bool multi = e->cfg.world_size > 1;
   switch (e->algo) {
     case NBX_ALL_PAIRS: {
-      const bool fuse = !(e->cfg.flags & NBX_FLAG_NO_FUSED_INTEGRATE);
+      // multi-GPU: the force functions leave the FULL acceleration array on every rank (symmetric kernel: all-reduce of
+      // the per-rank sums; ordered kernel: all-gather of the per-rank target shards), then every rank integrates all
+      // bodies — the whole state_t stays replicated and any rank can serve nbx_download / nbx_calc_energies.
+      const bool fuse = !(e->cfg.flags & NBX_FLAG_NO_FUSED_INTEGRATE) && (!multi || all_pairs_sym_enabled(e));
       NBX_TRY(all_pairs_force(e, fuse));
       if (!fuse) NBX_TRY(accelerate_step(e));
-      break;
+      return NBX_OK;
     }
     case NBX_ALL_PAIRS_COLLAPSED:
       NBX_TRY(all_pairs_collapsed_force(e));
       NBX_TRY(accelerate_step(e));
-      break;
+      return NBX_OK;
     case NBX_BVH:
       NBX_TRY(bvh_bounding_box(e));
       NBX_TRY(bvh_hilbert_sort(e));
       NBX_TRY(bvh_build_tree(e));
-      NBX_TRY(bvh_compute_force(e));
-      if (multi) NBX_TRY(comm_allgather(e, e->a));  // a[tb,te) of every rank -> full a everywhere
+      NBX_TRY(bvh_compute_force(e));  // all-gathers a[tb,te) of every rank -> full a everywhere
       NBX_TRY(accelerate_step(e));
       return NBX_OK;
     case NBX_OCTREE:
@@ -201,8 +203,6 @@ static int one_step(nbx_engine* e) {
       return NBX_OK;
     default: return fail(NBX_ERR_INVALID, "unknown algorithm");
   }
-  if (multi && !all_pairs_sym_enabled(e)) NBX_TRY(comm_allgather_positions(e));
-  return NBX_OK;
 }
 
 static void collect_phase_times(nbx_engine* e) {

@@ -190,8 +190,7 @@ int octree_get_canonical(nbx_engine* e, uint64_t* count, uint32_t* depth, uint64
 // nbx_comm.cu
 int comm_unique_id(void* id128);
 int comm_init_rank(nbx_engine* e, const void* id128);
-int comm_allgather_positions(nbx_engine* e);  // all-gather xm[cur] shards (chunk records per rank), in place
-int comm_allgather(nbx_engine* e, void* vec4_array);
+int comm_allgather(nbx_engine* e, void* vec4_array);  // in place: rank r contributes records [r*chunk, (r+1)*chunk)
 int comm_allreduce_sum(nbx_engine* e, void* buffer, size_t count);  // in place, `count` elements of the engine's precision
 void comm_destroy(nbx_engine* e);
 
