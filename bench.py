@@ -376,7 +376,9 @@ def roofline_tree(ctx, cfg, n, dim, dt, ph, st, targets, clk):
     prof = ctx.profile_consts.get(key, {})
     mhz = (clk or {}).get("sm_mhz") or (clk or {}).get("sm_max_mhz") or ctx.peaks.get("sm_max_mhz") or 1965.0
     peak = ctx.sm_count * 4 * mhz * 1e6 / 1e9  # G warp-instructions/s
-    ips = prof.get("inst_per_warp_step")
+    # the constant belongs to one kernel instantiation: the bvh walk serves 32, 64 or 128 bodies per warp step depending on
+    # the problem size, only the captured variant has a committed instruction count
+    ips = prof.get("inst_per_warp_step") if prof.get("bodies_per_warp_step") == st["width"] else None
     t = ph.get("traverse")
     achieved = ips * st["warp_steps"] / (t * 1e-3) / 1e9 if ips and t else None
     hbm_peak = ctx.peaks.get("hbm_gbs", 6650.0)
@@ -385,7 +387,7 @@ def roofline_tree(ctx, cfg, n, dim, dt, ph, st, targets, clk):
          "kernel_ms": t, "inst_per_step": ips, "inst_per_step_source": prof.get("source"),
          "warp_steps": st["warp_steps"], "tests_per_body": st["node_visits"] / max(1, targets),
          "interactions_per_body": st["interactions"] / max(1, targets),
-         "lane_utilisation": st["node_visits"] / max(1, 32 * st["warp_steps"]),
+         "bodies_per_warp_step": st["width"], "lane_utilisation": st["node_visits"] / max(1, st["width"] * st["warp_steps"]),
          "traffic": prof.get("dram_bytes") if prof.get("n") == n else None,
          "l2_hit_pct": prof.get("l2_hit_pct"),
          "note": f"peak = {ctx.sm_count} SMs x 4 schedulers x {mhz:.0f} MHz (SM clock sampled during the timed region); "
@@ -462,11 +464,18 @@ def measure(ctx, cfg, steps, warmup, want_e2e, want_cpu, s=None):
         lib = nbx.lib()
 
         def e2e_step():
-            eng.upload(host["m"], host["x"], host["v"], host["a"], host["ao"])   # H2D of the step's inputs
-            eng.step(1)
-            # D2H of the result, straight into the pinned buffer the next step uploads from (nbx_upload has returned, so
-            # the old contents are no longer needed)
-            rc = lib.nbx_download(eng._h, None, host["x"].ctypes.data_as(C.c_void_p), None, None, None)
+            # H2D of the step's inputs / D2H of the result, straight into the pinned buffer the next step uploads from
+            # (nbx_upload has returned, so the old contents are no longer needed). On N GPUs every rank moves ITS shard
+            # of the bodies over PCIe (nbx_upload_shard all-gathers the shards over NVLink): the job still moves every
+            # input byte to the devices and every result byte back once per step.
+            if world > 1:
+                eng.upload_shard(host["m"], host["x"], host["v"], host["a"], host["ao"])
+                eng.step(1)
+                rc = lib.nbx_download_shard(eng._h, None, host["x"].ctypes.data_as(C.c_void_p), None, None, None)
+            else:
+                eng.upload(host["m"], host["x"], host["v"], host["a"], host["ao"])
+                eng.step(1)
+                rc = lib.nbx_download(eng._h, None, host["x"].ctypes.data_as(C.c_void_p), None, None, None)
             assert rc == 0
         for _ in range(max(1, warmup - 1)):
             e2e_step()
@@ -479,7 +488,10 @@ def measure(ctx, cfg, steps, warmup, want_e2e, want_cpu, s=None):
         isz = np.dtype(dt).itemsize
         e2e = {"value": units_per_step(cfg, n) * steps / e2e_s, "unit": unit,
                "h2d_bytes_per_step": int(n * (1 + 4 * dim) * isz), "d2h_bytes_per_step": int(n * dim * isz),
-               "ms_per_step": 1e3 * e2e_s / steps}
+               "ms_per_step": 1e3 * e2e_s / steps,
+               "io": "nbx_upload + nbx_download, pinned host buffers" if world == 1 else
+                     f"nbx_upload_shard + nbx_download_shard: each rank moves its 1/{world} of the bytes over PCIe, shards "
+                     "all-gathered over NVLink (bytes below are the job totals)"}
     eng.close()
 
     if cfg.algorithm == "all-pairs" and n >= 16384:
@@ -616,6 +628,26 @@ def verify_multi(ctx, cases=VERIFY_CASES, log=None):
         if log and (ctx.rank == 0 or not good):
             log(f"[rank {ctx.rank}/{ctx.world}] {name}: {'OK' if good else 'FAIL'} {detail}")
     os.environ.pop("NBX_OCT_HILBERT", None)
+    # sharded I/O: every rank uploads only its shard; afterwards every rank must hold the complete state
+    for prec, dim, n in (("float", 3, 100003), ("double", 2, 5001)):
+        cfg = argparse.Namespace(algorithm="all-pairs", precision=prec, dim=dim, n=n, theta=0.5)
+        s = make_state(n, np.float32 if prec == "float" else np.float64, dim)
+        s["a"] = s["v"] * 3
+        s["ao"] = s["x"] * 0.5
+        with ctx.new_engine({**s, **{k: np.zeros_like(s[k]) for k in ("m", "x", "v", "a", "ao")}}, cfg, multi=True) as e:
+            e.upload_shard(s["m"], s["x"], s["v"], s["a"], s["ao"])
+            full = e.download()
+            part = {k: np.full_like(s[k], -7) for k in ("m", "x", "v", "a", "ao")}
+            e.download_shard_into(**part)
+        lo, hi = nbx.shard_bounds(n, ctx.rank, ctx.world)
+        good = all(full[k].tobytes() == s[k].tobytes() for k in ("m", "x", "v", "a", "ao"))
+        good &= all(part[k][lo:hi].tobytes() == s[k][lo:hi].tobytes() and (part[k][:lo] == -7).all() and (part[k][hi:] == -7).all()
+                    for k in ("m", "x", "v", "a", "ao"))
+        ok_all &= bool(good)
+        name = f"shard upload/download {prec} {dim}-D n={n}"
+        results.append({"case": name, "ok": bool(good)})
+        if log and (ctx.rank == 0 or not good):
+            log(f"[rank {ctx.rank}/{ctx.world}] {name}: {'OK' if good else 'FAIL'}")
     t = torch.tensor([1 if ok_all else 0], device="cuda")
     if ctx.dist:
         ctx.dist.all_reduce(t, op=ctx.dist.ReduceOp.MIN)

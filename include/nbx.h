@@ -12,6 +12,9 @@
  *
  * Threading: one caller thread per engine; every call returns after its work is enqueued on the engine's
  * CUDA stream, calls that copy to host memory return after the copy has completed. nbx_sync() blocks.
+ * One exception: every octree build (nbx_octree_build, and each step of nbx_step on an NBX_OCTREE engine) waits once for
+ * the device, after the tree records are emitted, to learn whether the bodies were separated within the key depth and
+ * the cells fit — an unusable tree is reported as NBX_ERR_CAPACITY from that call, before any force kernel walks it.
  * Errors: every function returns NBX_OK (0) or a negative code; nbx_last_error() gives the message of the
  * last failure on the calling thread. There is NO CPU fallback: without a CUDA device nbx_create fails.
  */
@@ -85,6 +88,13 @@ int nbx_destroy(nbx_engine* e);
  * may be NULL to skip that array. */
 int nbx_upload(nbx_engine* e, const void* m, const void* x, const void* v, const void* a, const void* ao);
 int nbx_download(nbx_engine* e, void* m, void* x, void* v, void* a, void* ao);
+/* multi-GPU I/O: the pointers address the FULL host arrays as above, but only this rank's shard of bodies
+ * [rank*ceil(n/world), (rank+1)*ceil(n/world)) is read / written. nbx_upload_shard then all-gathers the shards on the
+ * device (NCCL over NVLink), so every rank still ends up with the complete replicated state while each sends only
+ * 1/world of the bytes over PCIe; it is a collective: every rank of the communicator must call it with the same set of
+ * non-NULL arrays. With world_size 1 both are nbx_upload / nbx_download. */
+int nbx_upload_shard(nbx_engine* e, const void* m, const void* x, const void* v, const void* a, const void* ao);
+int nbx_download_shard(nbx_engine* e, void* m, void* x, void* v, void* a, void* ao);
 
 /* replaces: the `kernels()` lambda of run_all_pairs / run_octree / run_bvh (src/all_pairs.h:86-92,
  * src/octree.h:321-328, src/bvh.h:382-397): `steps` x (force + accelerate_step), device resident. */
@@ -151,6 +161,9 @@ int nbx_measure_fma_peak(int device, int precision, double* tflops);
  * of warp-level steps (= records loaded per warp). Used for the HBM/L2 roofline of the walk: algorithmic bytes =
  * node_visits x node record size. */
 int nbx_traversal_stats(nbx_engine* e, uint64_t* node_visits, uint64_t* interactions, uint64_t* warp_steps);
+/* bodies a warp of the tree walk serves per step (octree: 32, one per lane; bvh: 32 x bodies per lane): the denominator
+ * of the lane utilisation node_visits / (warp_steps x width). */
+int nbx_walk_width(nbx_engine* e, uint32_t* bodies_per_warp_step);
 /* counters of the engine since creation: kernels launched by this library, bytes copied H2D / D2H */
 int nbx_get_counters(nbx_engine* e, uint64_t* kernel_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 /* per-phase device time (ms) of the last nbx_step* call's LAST step;

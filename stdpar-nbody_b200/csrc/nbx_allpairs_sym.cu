@@ -19,6 +19,7 @@
 // accelerations and every rank integrates all bodies (replicated state, no position exchange).
 #include <cfloat>
 #include <cstdlib>
+#include <string>
 
 #include "nbx_device.cuh"
 #include "nbx_internal.cuh"
@@ -37,8 +38,7 @@ struct SymArgs {
   const vec4_t<T>* xm;
   const float* soa;   // packed float kernel only: [4][soa_stride] = x[], y[], z[], m[] of the same bodies
   uint64_t soa_stride;
-  vec4_t<T>* P;       // [K][slab]
-  uint64_t slab;      // K * B (bodies, padded)
+  vec4_t<T>* P;       // [units of this rank][2][B]: action sums on the unit's I block, reaction sums on its J block
   uint32_t B, K;
   uint32_t unit_begin, unit_stride;
 };
@@ -144,8 +144,8 @@ __global__ void __launch_bounds__(256, MINB) all_pairs_sym_kernel(SymArgs<T> p) 
   if (tid == 0)
     for (int k = 0; k < SYM_STAGES && k < total; ++k) issue(k);
 
-  V4* Paction = p.P + uint64_t(J) * p.slab;  // actions on i in I caused by block J
-  V4* Preact  = p.P + uint64_t(I) * p.slab;  // reactions on j in J caused by block I
+  V4* Paction = p.P + uint64_t(2 * blockIdx.x) * p.B;      // actions on i in I caused by block J, indexed by i - I0
+  V4* Preact  = p.P + uint64_t(2 * blockIdx.x + 1) * p.B;  // reactions on j in J caused by block I, indexed by j - J0
 
   int k = 0;
   for (uint32_t isub = 0; isub < nsub; ++isub) {
@@ -201,56 +201,17 @@ __global__ void __launch_bounds__(256, MINB) all_pairs_sym_kernel(SymArgs<T> p) 
             }
             v[3 * jj] = rx; v[3 * jj + 1] = ry; v[3 * jj + 2] = rz;
           }
-          // transposed butterfly over the warp: 12 values -> 6 -> 3 per lane, then three plain stages; lanes 0, 8, 16, 24
-          // end up with the warp totals of bodies j0+0, j0+1, j0+2, j0+3 (fixed order => deterministic)
-          T w[6], u[3];
-          const bool hi16 = lane & 16, hi8 = lane & 8;
-#pragma unroll
-          for (int q = 0; q < 6; ++q) {
-            const T mine = hi16 ? v[6 + q] : v[q];
-            const T send = hi16 ? v[q] : v[6 + q];
-            w[q] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
-          }
-#pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            const T mine = hi8 ? w[3 + q] : w[q];
-            const T send = hi8 ? w[q] : w[3 + q];
-            u[q] = mine + __shfl_xor_sync(0xffffffffu, send, 8);
-          }
-#pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            u[q] += __shfl_xor_sync(0xffffffffu, u[q], 4);
-            u[q] += __shfl_xor_sync(0xffffffffu, u[q], 2);
-            u[q] += __shfl_xor_sync(0xffffffffu, u[q], 1);
-          }
-          if ((lane & 7) == 0) {
-            const int jsel = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
-            T* dst = racc + (size_t(warp) * SYM_JT + j0 + jsel) * 3;
-            dst[0] = u[0]; dst[1] = u[1]; dst[2] = u[2];
-          }
+          sym_reduce4<T>(v, lane, racc, warp, j0);
         }
         __syncthreads();
-        {  // the CTA is the only writer of P[I][j in J]: accumulate over the sub-blocks of I in order
-          T rx = T(0), ry = T(0), rz = T(0);
-#pragma unroll
-          for (int wq = 0; wq < SYM_WARPS; ++wq) {
-            const T* src = racc + (size_t(wq) * SYM_JT + tid) * 3;
-            rx += src[0]; ry += src[1]; rz += src[2];
-          }
-          V4* dst = Preact + J0 + jt * SYM_JT + tid;
-          if (isub != 0) {
-            const V4 old = ldcg_v4(dst);
-            rx += old.x; ry += old.y; rz += old.z;
-          }
-          stcg_v4(dst, make_v4<T>(rx, ry, rz, T(0)));
-        }
+        sym_flush_reactions<T>(racc, Preact + jt * SYM_JT + tid, tid, isub != 0);
       }
       __syncthreads();  // tile (and racc) free again
       if (tid == 0 && k + SYM_STAGES < total) issue(k + SYM_STAGES);
     }
 #pragma unroll
     for (int t = 0; t < RI; ++t)
-      stcg_v4(Paction + I0 + isub * (256 * RI) + t * 256 + tid, make_v4<T>(ax[t], ay[t], az[t], T(0)));
+      stcg_v4(Paction + isub * (256 * RI) + t * 256 + tid, make_v4<T>(ax[t], ay[t], az[t], T(0)));
   }
 }
 
@@ -261,8 +222,7 @@ __global__ void __launch_bounds__(256, MINB) all_pairs_sym_kernel(SymArgs<T> p) 
 // copy of the positions) so that a j pair is one LDS.64 per component; the i bodies are held as duplicated pairs.
 template <int D, int RI, int MINB>
 __global__ void __launch_bounds__(256, MINB) all_pairs_sym_packed_kernel(SymArgs<float> p) {
-  using T               = float;
-  constexpr bool PACKED = true;
+  using T = float;
   using V4 = vec4_t<T>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   V4* tiles      = reinterpret_cast<V4*>(smem_raw);
@@ -288,41 +248,32 @@ __global__ void __launch_bounds__(256, MINB) all_pairs_sym_packed_kernel(SymArgs
     const int stage = k % SYM_STAGES;
     mbar_expect_tx(&bars[stage], TILE_BYTES);
     const size_t j = size_t(J0) + size_t(k % int(ntile)) * SYM_JT;
-    if constexpr (PACKED) {
-      float* dst = reinterpret_cast<float*>(tiles + size_t(stage) * SYM_JT);  // [4][SYM_JT] floats in the same 4 KB
+    float* dst     = reinterpret_cast<float*>(tiles + size_t(stage) * SYM_JT);  // [4][SYM_JT] floats in the same 4 KB
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tma_load_1d(dst + c * SYM_JT, p.soa + c * p.soa_stride + j, TILE_BYTES / 4, &bars[stage]);
-    } else {
-      tma_load_1d(tiles + size_t(stage) * SYM_JT, p.xm + j, TILE_BYTES, &bars[stage]);
-    }
+    for (int c = 0; c < 4; ++c) tma_load_1d(dst + c * SYM_JT, p.soa + c * p.soa_stride + j, TILE_BYTES / 4, &bars[stage]);
   };
   if (tid == 0)
     for (int k = 0; k < SYM_STAGES && k < total; ++k) issue(k);
 
-  V4* Paction = p.P + uint64_t(J) * p.slab;  // actions on i in I caused by block J
-  V4* Preact  = p.P + uint64_t(I) * p.slab;  // reactions on j in J caused by block I
+  V4* Paction = p.P + uint64_t(2 * blockIdx.x) * p.B;      // actions on i in I caused by block J, indexed by i - I0
+  V4* Preact  = p.P + uint64_t(2 * blockIdx.x + 1) * p.B;  // reactions on j in J caused by block I, indexed by j - J0
 
   int k = 0;
   for (uint32_t isub = 0; isub < nsub; ++isub) {
-    T xi[RI], yi[RI], zi[RI], mi[RI], ax[RI], ay[RI], az[RI];
-    float2 nx2[PACKED ? RI : 1], ny2[PACKED ? RI : 1], nz2[PACKED ? RI : 1], m2[PACKED ? RI : 1];  // (-x_i, -x_i) ... (m_i, m_i)
-    float2 ax2[PACKED ? RI : 1], ay2[PACKED ? RI : 1], az2[PACKED ? RI : 1];                       // even-j / odd-j partial sums
+    float2 nx2[RI], ny2[RI], nz2[RI], m2[RI];  // (-x_i, -x_i) ... (m_i, m_i)
+    float2 ax2[RI], ay2[RI], az2[RI];          // even-j / odd-j partial sums
 #pragma unroll
     for (int t = 0; t < RI; ++t) {
       const V4 b = p.xm[I0 + isub * (256 * RI) + t * 256 + tid];
-      xi[t] = b.x; yi[t] = b.y; zi[t] = b.z; mi[t] = b.w;
-      ax[t] = ay[t] = az[t] = T(0);
-      if constexpr (PACKED) {
-        nx2[t] = make_float2(-b.x, -b.x); ny2[t] = make_float2(-b.y, -b.y); nz2[t] = make_float2(-b.z, -b.z);
-        m2[t]  = make_float2(b.w, b.w);
-        ax2[t] = ay2[t] = az2[t] = make_float2(0.f, 0.f);
-      }
+      nx2[t] = make_float2(-b.x, -b.x); ny2[t] = make_float2(-b.y, -b.y); nz2[t] = make_float2(-b.z, -b.z);
+      m2[t]  = make_float2(b.w, b.w);
+      ax2[t] = ay2[t] = az2[t] = make_float2(0.f, 0.f);
     }
     for (uint32_t jt = 0; jt < ntile; ++jt, ++k) {
       const int stage = k % SYM_STAGES;
       mbar_wait(&bars[stage], (k / SYM_STAGES) & 1);
       const V4* tile = tiles + size_t(stage) * SYM_JT;
-      if constexpr (PACKED) {
+      {
         const float* tx = reinterpret_cast<const float*>(tile);
         const float *ty = tx + SYM_JT, *tz = tx + 2 * SYM_JT, *tm = tx + 3 * SYM_JT;
         if (diag) {
@@ -373,62 +324,16 @@ __global__ void __launch_bounds__(256, MINB) all_pairs_sym_packed_kernel(SymArgs
             sym_reduce4<T>(v, lane, racc, warp, j0);
           }
           __syncthreads();
-          sym_flush_reactions<T>(racc, Preact + J0 + jt * SYM_JT + tid, tid, isub != 0);
+          sym_flush_reactions<T>(racc, Preact + jt * SYM_JT + tid, tid, isub != 0);
         }
-      } else if (diag) {
-#pragma unroll 4
-        for (int j = 0; j < SYM_JT; ++j) {
-          const V4 b = tile[j];
-#pragma unroll
-          for (int t = 0; t < RI; ++t) {
-            T dx = b.x - xi[t], dy = b.y - yi[t];
-            T d2 = fma(dy, dy, sq_plus_tiny(dx));
-            T dz = T(0);
-            if (D == 3) { dz = b.z - zi[t]; d2 = fma(dz, dz, d2); }
-            T s   = b.w * inv_dist3_pos(d2);
-            ax[t] = fma(dx, s, ax[t]);
-            ay[t] = fma(dy, s, ay[t]);
-            if (D == 3) az[t] = fma(dz, s, az[t]);
-          }
-        }
-      } else {
-#pragma unroll 1
-        for (int j0 = 0; j0 < SYM_JT; j0 += 4) {
-          T v[12];
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const V4 b = tile[j0 + jj];
-            T rx = T(0), ry = T(0), rz = T(0);
-#pragma unroll
-            for (int t = 0; t < RI; ++t) {
-              T dx = b.x - xi[t], dy = b.y - yi[t];
-              T d2 = fma(dy, dy, sq_plus_tiny(dx));
-              T dz = T(0);
-              if (D == 3) { dz = b.z - zi[t]; d2 = fma(dz, dz, d2); }
-              const T inv = inv_dist3_pos(d2);
-              const T si = b.w * inv, sj = mi[t] * inv;
-              ax[t] = fma(dx, si, ax[t]);
-              ay[t] = fma(dy, si, ay[t]);
-              if (D == 3) az[t] = fma(dz, si, az[t]);
-              rx = fma(-dx, sj, rx);
-              ry = fma(-dy, sj, ry);
-              if (D == 3) rz = fma(-dz, sj, rz);
-            }
-            v[3 * jj] = rx; v[3 * jj + 1] = ry; v[3 * jj + 2] = rz;
-          }
-          sym_reduce4<T>(v, lane, racc, warp, j0);
-        }
-        __syncthreads();
-        sym_flush_reactions<T>(racc, Preact + J0 + jt * SYM_JT + tid, tid, isub != 0);
       }
       __syncthreads();  // tile (and racc) free again
       if (tid == 0 && k + SYM_STAGES < total) issue(k + SYM_STAGES);
     }
 #pragma unroll
-    for (int t = 0; t < RI; ++t) {
-      if constexpr (PACKED) { ax[t] = ax2[t].x + ax2[t].y; ay[t] = ay2[t].x + ay2[t].y; az[t] = az2[t].x + az2[t].y; }
-      stcg_v4(Paction + I0 + isub * (256 * RI) + t * 256 + tid, make_v4<T>(ax[t], ay[t], az[t], T(0)));
-    }
+    for (int t = 0; t < RI; ++t)
+      stcg_v4(Paction + isub * (256 * RI) + t * 256 + tid,
+              make_v4<T>(ax2[t].x + ax2[t].y, ay2[t].x + ay2[t].y, az2[t].x + az2[t].y, T(0)));
   }
 }
 
@@ -452,20 +357,24 @@ __device__ __forceinline__ void sym_store(const LeapArgs<T>& leap, uint32_t b, T
   leap.a[b] = q;
 }
 
-// a[b] = c * sum_K P[K][b] (K ascending, only the units this rank computed), optionally fused with the leapfrog
+// a[b] = c * (sum over the units (k, block of b), k ascending, that THIS rank computed), optionally fused with the leapfrog.
+// Unit u = (lo, hi) is the rank's local unit (u - unit_begin) / unit_stride; body b gets the unit's action sums when its
+// block is the lower index (or the diagonal), the reaction sums when it is the higher one.
 template <typename T, int D>
-__global__ void __launch_bounds__(256) sym_reduce_kernel(const vec4_t<T>* __restrict__ P, uint64_t slab, uint32_t B, uint32_t K, uint32_t n,
+__global__ void __launch_bounds__(256) sym_reduce_kernel(const vec4_t<T>* __restrict__ P, uint32_t B, uint32_t K, uint32_t n,
                                                          uint32_t unit_begin, uint32_t unit_stride, T c, int finish, int fuse, int nc,
                                                          vec4_t<T>* __restrict__ asum, LeapArgs<T> leap) {
   const uint32_t b = blockIdx.x * 256 + threadIdx.x;
   if (b >= n) return;
   const uint32_t Bb = (blockIdx.x * 256) / B;  // B is a multiple of 256: uniform per CTA
+  const uint32_t ob = b - Bb * B;
   T sx = 0, sy = 0, sz = 0;
   for (uint32_t k = 0; k < K; ++k) {
     const uint32_t lo = k < Bb ? k : Bb, hi = k < Bb ? Bb : k;
     const uint32_t u  = uint32_t(uint64_t(hi) * (hi + 1) / 2) + lo;
     if (u < unit_begin || (u - unit_begin) % unit_stride) continue;  // another rank's unit
-    const vec4_t<T> q = ldcg_v4(P + uint64_t(k) * slab + b);
+    const uint64_t lu = (u - unit_begin) / unit_stride;
+    const vec4_t<T> q = ldcg_v4(P + (2 * lu + (k < Bb ? 1 : 0)) * B + ob);
     sx += q.x; sy += q.y; sz += q.z;
   }
   if (!finish) {
@@ -487,7 +396,7 @@ __global__ void __launch_bounds__(256) sym_finish_kernel(const vec4_t<T>* __rest
 
 struct SymState {
   uint32_t B = 0, K = 0;
-  uint64_t slab = 0;
+  uint64_t slab = 0;         // K * B: bodies covered by the blocks (>= n)
   void* P    = nullptr;
   void* asum = nullptr;
   float* soa = nullptr;      // packed float kernel: x[], y[], z[], m[] copy of the current positions, refreshed every step
@@ -507,26 +416,49 @@ __global__ void __launch_bounds__(256) aos_to_soa_kernel(const float4* __restric
 
 // B: 1024 below n = 2^17 (K = ceil(n / B) <= 128: enough (I, J) units for 148 SMs from n = 16384 on), above that
 // 2048 * ceil(n / 2^19), a multiple of 256 * 8 so that the kernels with 8 targets per thread apply; K <= 256 up to n = 2^27.
-// NBX_SYM_BLOCK1024=1 restores the former rule 1024 * ceil(n / 2^18) (experiments).
-uint32_t all_pairs_sym_block(uint32_t n) {
+// On several GPUs the units of a rank should still fill >= 40 waves of its 2 x 148 resident CTAs, or the last partial
+// wave shows (measured at n = 1 M on 8 GPUs with B = 4096: 12.7 waves, 40.3 ms instead of 38.8): B shrinks (in steps of
+// 2048) until K(K+1)/2 >= 40 * 296 * world. NBX_SYM_BLOCK1024=1 restores the former rule 1024 * ceil(n / 2^18) (experiments).
+uint32_t all_pairs_sym_block(uint32_t n, int world) {
   static const bool old_rule = [] { const char* v = getenv("NBX_SYM_BLOCK1024"); return v && atoi(v); }();
   if (n < (1u << 17) || old_rule) {
     const uint32_t mult = (n + (1u << 18) - 1) >> 18;
     return 1024u * (mult ? mult : 1);
   }
-  return 2048u * ((n + (1u << 19) - 1) >> 19);
+  uint32_t B = 2048u * ((n + (1u << 19) - 1) >> 19);
+  if (world > 1) {
+    const uint64_t want = uint64_t(40) * 296 * uint64_t(world);
+    while (B > 2048u) {
+      const uint64_t K = (uint64_t(n) + B - 1) / B;
+      if (K * (K + 1) / 2 >= want) break;
+      B -= 2048u;
+    }
+  }
+  return B;
 }
 
 template <typename T, int D, int RI, int MINB, bool PACKED = false>
 static int sym_launch(nbx_engine* e, bool fuse, int nc) {
   SymState* s = static_cast<SymState*>(e->sym);
+  const uint32_t world = uint32_t(e->cfg.world_size), rank = uint32_t(e->cfg.rank);
   if (!s) {
     s       = new SymState();
     e->sym  = s;
-    s->B    = all_pairs_sym_block(e->n);
+    s->B    = all_pairs_sym_block(e->n, e->cfg.world_size);
     s->K    = (e->n + s->B - 1) / s->B;
     s->slab = uint64_t(s->K) * s->B;
-    NBX_CUDA(cudaMalloc(&s->P, sizeof(vec4_t<T>) * s->slab * s->K));
+    // partial sums of THIS rank's units only: 2 x B records per unit = about K * n / world records (3.9 GB at n = 1 M float
+    // on one GPU). Checked against the free memory first, so a large n fails with a clear message instead of a bare
+    // cudaMalloc error (the ordered kernel, NBX_FLAG_ALLPAIRS_ORDERED, needs no such buffer).
+    const uint64_t units = uint64_t(s->K) * (s->K + 1) / 2;
+    const uint64_t mine  = (units > rank ? units - rank + world - 1 : 0) / world;
+    const size_t bytes   = sizeof(vec4_t<T>) * size_t(2) * s->B * size_t(mine ? mine : 1);
+    size_t free_b = 0, total_b = 0;
+    NBX_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    if (bytes + (size_t(512) << 20) > free_b)
+      return fail(NBX_ERR_CAPACITY, "symmetric all-pairs: the partial-sum buffer needs " + std::to_string(bytes >> 20) + " MiB, " +
+                                        std::to_string(free_b >> 20) + " MiB are free; create the engine with NBX_FLAG_ALLPAIRS_ORDERED");
+    NBX_CUDA(cudaMalloc(&s->P, bytes));
     NBX_CUDA(cudaMalloc(&s->asum, sizeof(vec4_t<T>) * e->n_pad));
   }
   if constexpr (PACKED) {
@@ -546,7 +478,6 @@ static int sym_launch(nbx_engine* e, bool fuse, int nc) {
   }();
   const size_t smem = size_t(SYM_STAGES) * SYM_JT * sizeof(vec4_t<T>) + size_t(SYM_WARPS) * SYM_JT * 3 * sizeof(T) + SYM_STAGES * sizeof(uint64_t);
   NBX_TRY(ensure_dynamic_smem(e, kern, smem));
-  const uint32_t world = uint32_t(e->cfg.world_size), rank = uint32_t(e->cfg.rank);
   const uint64_t units = uint64_t(s->K) * (s->K + 1) / 2;
   const uint32_t mine  = uint32_t((units > rank ? units - rank + world - 1 : 0) / world);
   SymArgs<T> p;
@@ -554,7 +485,6 @@ static int sym_launch(nbx_engine* e, bool fuse, int nc) {
   p.soa        = s->soa;
   p.soa_stride = s->soa_stride;
   p.P  = static_cast<vec4_t<T>*>(s->P);
-  p.slab = s->slab;
   p.B = s->B;
   p.K = s->K;
   p.unit_begin  = rank;
@@ -570,11 +500,11 @@ static int sym_launch(nbx_engine* e, bool fuse, int nc) {
   leap.dt = T(e->cfg.dt);
   const unsigned gb = (e->n + 255) / 256;
   if (world == 1) {
-    sym_reduce_kernel<T, D><<<gb, 256, 0, e->stream>>>(p.P, s->slab, s->B, s->K, e->n, 0, 1, T(e->cfg.G), 1, fuse ? 1 : 0, nc,
+    sym_reduce_kernel<T, D><<<gb, 256, 0, e->stream>>>(p.P, s->B, s->K, e->n, 0, 1, T(e->cfg.G), 1, fuse ? 1 : 0, nc,
                                                       static_cast<vec4_t<T>*>(s->asum), leap);
     e->launches++;
   } else {
-    sym_reduce_kernel<T, D><<<gb, 256, 0, e->stream>>>(p.P, s->slab, s->B, s->K, e->n, rank, world, T(e->cfg.G), 0, 0, nc,
+    sym_reduce_kernel<T, D><<<gb, 256, 0, e->stream>>>(p.P, s->B, s->K, e->n, rank, world, T(e->cfg.G), 0, 0, nc,
                                                       static_cast<vec4_t<T>*>(s->asum), leap);
     NBX_TRY(comm_allreduce_sum(e, s->asum, size_t(e->n) * 4));
     sym_finish_kernel<T, D><<<gb, 256, 0, e->stream>>>(static_cast<const vec4_t<T>*>(s->asum), e->n, T(e->cfg.G), fuse ? 1 : 0, nc, leap);
@@ -597,7 +527,7 @@ int all_pairs_sym_force(nbx_engine* e, bool fuse, int collapsed_nc) {
     // n = 1 M: scalar 361 ms, packed x4 321 ms, packed x8 311 ms per step. NBX_SYM_PACKED=0|1|2 forces scalar / x4 / x8.
     const char* env  = getenv("NBX_SYM_PACKED");
     const int forced = env ? atoi(env) : -1;
-    const bool can8 = all_pairs_sym_block(e->n) % 2048u == 0;
+    const bool can8 = all_pairs_sym_block(e->n, e->cfg.world_size) % 2048u == 0;
     const int packed = forced >= 0 ? (forced == 2 && !can8 ? 1 : forced) : (can8 ? 2 : 1);
     if (packed == 2) return e->dim == 2 ? sym_launch<float, 2, 8, 2, true>(e, fuse, collapsed_nc) : sym_launch<float, 3, 8, 2, true>(e, fuse, collapsed_nc);
     if (packed == 1) return e->dim == 2 ? sym_launch<float, 2, 4, 2, true>(e, fuse, collapsed_nc) : sym_launch<float, 3, 4, 2, true>(e, fuse, collapsed_nc);
@@ -609,7 +539,7 @@ int all_pairs_sym_force(nbx_engine* e, bool fuse, int collapsed_nc) {
     // 8 targets per thread where B allows it: the butterfly and the tile flush are amortised over twice as many pairs
     // (n = 262144: 59.4 -> 56.9 ms per step, FP64-pipe fraction 0.68 -> 0.71). NBX_SYM_DOUBLE_RI=4 forces 4 (experiments).
     const char* env = getenv("NBX_SYM_DOUBLE_RI");
-    if (!(env && atoi(env) == 4) && all_pairs_sym_block(e->n) % 2048u == 0)
+    if (!(env && atoi(env) == 4) && all_pairs_sym_block(e->n, e->cfg.world_size) % 2048u == 0)
       return e->dim == 2 ? sym_launch<double, 2, 8, 1>(e, fuse, collapsed_nc) : sym_launch<double, 3, 8, 1>(e, fuse, collapsed_nc);
   }
   return e->dim == 2 ? sym_launch<double, 2, 4, 1>(e, fuse, collapsed_nc) : sym_launch<double, 3, 4, 1>(e, fuse, collapsed_nc);

@@ -33,6 +33,20 @@ __device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(
 __device__ __forceinline__ uint32_t to_u32_sat(float q) { return __float2uint_rz(q); }    // cvt.rzi.u32.f32 saturates
 __device__ __forceinline__ uint32_t to_u32_sat(double q) { return __double2uint_rz(q); }  // 
 
+// FP32x2 ops with EXPLICIT .rn in PTX: each half is rounded exactly like the scalar __fmul_rn / __fadd_rn, and neither
+// NVVM nor ptxas may contract them into an FFMA2 (the __fmul2_rn / __fadd2_rn intrinsics of sm_100_rt.h ARE contracted:
+// checked in SASS) — required wherever a decision must be bit-identical to the reference's unfused arithmetic.
+__device__ __forceinline__ float2 mul2_exact(float2 a, float2 b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 add2_exact(float2 a, float2 b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&r);
+}
+
 template <typename T>
 __host__ __device__ constexpr T eps_of() {
   return sizeof(T) == 4 ? T(FLT_EPSILON) : T(DBL_EPSILON);
@@ -48,6 +62,21 @@ struct Box {  // device-resident result of the bbox reduction
   T lo[4], hi[4], cell[4];
 };
 
+// The walk's view of a node: centre of mass + mass + width^2 in one 32 B (float) / 64 B (double) aligned record, so a
+// warp step costs one address computation and touches one sector-aligned line instead of two arrays.
+template <typename T>
+struct alignas(8 * sizeof(T)) WalkRec {
+  T x, y, z, m, w2, pad[3];
+};
+
+template <typename T>
+__device__ __forceinline__ WalkRec<T> make_rec(vec4_t<T> cm, T w2) {
+  WalkRec<T> r;
+  r.x = cm.x; r.y = cm.y; r.z = cm.z; r.m = cm.w; r.w2 = w2;
+  r.pad[0] = r.pad[1] = r.pad[2] = T(0);
+  return r;
+}
+
 template <typename T>
 struct BvhState {
   uint32_t levels = 0;      // log2(bit_ceil(n)); tree levels 0..levels-1, bodies are level `levels`
@@ -59,7 +88,8 @@ struct BvhState {
   uint32_t* perm   = nullptr;
   vec4_t<T>* node_m = nullptr;  // (com.x, com.y, com.z, mass)
   T* bw             = nullptr;
-  T* bw2            = nullptr;  // bw*bw (rounded once, as bvh.h:247 does per test): what the traversal loads
+  T* bw2            = nullptr;  // bw*bw (rounded once, as bvh.h:247 does per test)
+  WalkRec<T>* rec   = nullptr;  // what the traversal loads: (com, mass, bw^2) of node k in ONE aligned record
   vec4_t<T>* lo     = nullptr;
   vec4_t<T>* hi     = nullptr;
   bool have_box = false, sorted = false, built = false;
@@ -219,7 +249,7 @@ __device__ __forceinline__ T node_width(vec4_t<T> lo, vec4_t<T> hi) {  // bvh.h:
 // deepest tree level from pairs of bodies (bvh.h:178-207)
 template <typename T, int D>
 __global__ void __launch_bounds__(256) build_leaf_level_kernel(const vec4_t<T>* __restrict__ xm, uint32_t n, uint32_t first,
-                                                               uint32_t count, vec4_t<T>* node_m, T* bw, T* bw2, vec4_t<T>* lo,
+                                                               uint32_t count, vec4_t<T>* node_m, T* bw, WalkRec<T>* rec, vec4_t<T>* lo,
                                                                vec4_t<T>* hi) {
   uint32_t li = blockIdx.x * 256 + threadIdx.x;
   if (li >= count) return;
@@ -227,6 +257,7 @@ __global__ void __launch_bounds__(256) build_leaf_level_kernel(const vec4_t<T>* 
   const T tol = aabb_tol<T>();
   if (bl >= n) {
     node_m[i] = make_v4<T>(0, 0, 0, 0);  // dead node (mass 0); b/bw stay as allocated (zero)
+    rec[i]    = make_rec<T>(make_v4<T>(0, 0, 0, 0), T(0));
     return;
   }
   vec4_t<T> pl = xm[bl];
@@ -236,7 +267,7 @@ __global__ void __launch_bounds__(256) build_leaf_level_kernel(const vec4_t<T>* 
     vec4_t<T> bhi = make_v4<T>(add_rn(pl.x, tol), add_rn(pl.y, tol), D == 3 ? add_rn(pl.z, tol) : T(0), 0);
     lo[i] = blo; hi[i] = bhi;
     const T w = node_width<T, D>(blo, bhi);
-    bw[i] = w; bw2[i] = mul_rn(w, w);
+    bw[i] = w; rec[i] = make_rec<T>(pl, mul_rn(w, w));
     return;
   }
   vec4_t<T> pr = xm[br];
@@ -253,25 +284,24 @@ __global__ void __launch_bounds__(256) build_leaf_level_kernel(const vec4_t<T>* 
                              D == 3 ? add_rn(tmax(pl.z, pr.z), tol) : T(0), 0);
   lo[i] = blo; hi[i] = bhi;
   const T w = node_width<T, D>(blo, bhi);
-  bw[i] = w; bw2[i] = mul_rn(w, w);
+  bw[i] = w; rec[i] = make_rec<T>(c, mul_rn(w, w));
 }
 
-// one upper level from its children (bvh.h:210-243)
+// one node of an upper level from its children (bvh.h:210-243)
 template <typename T, int D>
-__global__ void __launch_bounds__(256) build_level_kernel(uint32_t first, uint32_t count, vec4_t<T>* node_m, T* bw, T* bw2,
-                                                          vec4_t<T>* lo, vec4_t<T>* hi) {
-  uint32_t li = blockIdx.x * 256 + threadIdx.x;
-  if (li >= count) return;
+__device__ __forceinline__ void build_node(uint32_t first, uint32_t count, uint32_t li, vec4_t<T>* node_m, T* bw, WalkRec<T>* rec,
+                                           vec4_t<T>* lo, vec4_t<T>* hi) {
   const uint32_t i = first + li, bl = li * 2 + first + count, br = bl + 1;
   vec4_t<T> ml = node_m[bl], mr = node_m[br];
   if (!(ml.w != T(0))) {
     node_m[i] = ml;
+    rec[i]    = make_rec<T>(ml, T(0));  // the reference leaves b/bw of dead nodes as allocated (zero)
     return;
   }
   if (!(mr.w != T(0))) {
     node_m[i] = ml;
     lo[i] = lo[bl]; hi[i] = hi[bl];
-    bw[i] = bw[bl]; bw2[i] = bw2[bl];
+    bw[i] = bw[bl]; rec[i] = rec[bl];
     return;
   }
   T mass = add_rn(ml.w, mr.w);
@@ -286,7 +316,27 @@ __global__ void __launch_bounds__(256) build_level_kernel(uint32_t first, uint32
   vec4_t<T> bhi = make_v4<T>(tmax(h0.x, h1.x), tmax(h0.y, h1.y), D == 3 ? tmax(h0.z, h1.z) : T(0), 0);
   lo[i] = blo; hi[i] = bhi;
   const T w = node_width<T, D>(blo, bhi);
-  bw[i] = w; bw2[i] = mul_rn(w, w);
+  bw[i] = w; rec[i] = make_rec<T>(c, mul_rn(w, w));
+}
+
+template <typename T, int D>
+__global__ void __launch_bounds__(256) build_level_kernel(uint32_t first, uint32_t count, vec4_t<T>* node_m, T* bw, WalkRec<T>* rec,
+                                                          vec4_t<T>* lo, vec4_t<T>* hi) {
+  const uint32_t li = blockIdx.x * 256 + threadIdx.x;
+  if (li < count) build_node<T, D>(first, count, li, node_m, bw, rec, lo, hi);
+}
+
+// the top of the tree, levels `top` .. 0 (at most 1024 nodes each), in ONE launch: a single CTA walks up level by level
+// (the reference launches one parallel algorithm per level, bvh.h:210-243)
+constexpr uint32_t BVH_TOP_LEVEL = 10;
+template <typename T, int D>
+__global__ void __launch_bounds__(1024) build_top_levels_kernel(int top, vec4_t<T>* node_m, T* bw, WalkRec<T>* rec, vec4_t<T>* lo,
+                                                                vec4_t<T>* hi) {
+  for (int l = top; l >= 0; --l) {
+    const uint32_t count = 1u << l;
+    if (threadIdx.x < count) build_node<T, D>(count - 1, count, threadIdx.x, node_m, bw, rec, lo, hi);
+    __syncthreads();  // the next level reads what this one wrote (same CTA: visible after the barrier)
+  }
 }
 
 // ---- K16 traversal ------------------------------------------------------------------------------------------------
@@ -359,27 +409,32 @@ __global__ void __launch_bounds__(128) bvh_force_kernel(const vec4_t<T>* __restr
 // WARP-COOPERATIVE version of the same walk (used when the leaf offsets fit 27 bits): each lane keeps the reference's
 // per-body state machine — its progress `covered` (= num_covered_particles, bvh.h:267) and the level of the node it wants
 // next; the node index follows from both: k = 2^level - 1 + (covered >> (levels - level)). Every step the warp takes the
-// smallest (covered, level) key over its lanes with one REDUX.MIN, loads THAT node once (warp-uniform address), and only
-// the lanes that asked for it act on it. The warp therefore walks the union of its lanes' paths in leaf order; each lane
+// smallest (covered, level) key over its bodies with one REDUX.MIN, loads THAT node once (warp-uniform address), and only
+// the bodies that asked for it act on it. The warp therefore walks the union of its bodies' paths in leaf order; each body
 // performs exactly the reference's sequence of tests and interactions.
 //
-// The per-lane state is folded into ONE word. `covered` is always even (nodes cover >= 2 leaves, the
+// The per-body state is folded into ONE word. `covered` is always even (nodes cover >= 2 leaves, the
 // body level covers 2), so key = (covered << 4) | level holds covered <= 2^27 without overflow. The key only ever grows:
-// opening node (covered, level) goes to (covered, level + 1) = key + 1 — which no other lane can be below, so the update
+// opening node (covered, level) goes to (covered, level + 1) = key + 1 — which no other body can be below, so the update
 // is key = max(key, candidate) with a warp-uniform candidate and needs no "is this my node" masking — and accepting adds
 // 2^(levels-level) leaves minus one level for a right child (sibling for a left child). The acceptance test is evaluated
-// by every lane (the node loads are warp-uniform anyway); only the accumulation is predicated. A lane is finished when
+// for every body (the node loads are warp-uniform anyway); only the accumulation is predicated. A body is finished when
 // covered >= n, i.e. key >= nlim; the warp stops when the minimum is.
-template <typename T, int D, bool COUNT = false>
-__global__ void __launch_bounds__(128) bvh_force_key_kernel(const vec4_t<T>* __restrict__ xm, const vec4_t<T>* __restrict__ node_m1,
-                                                            const T* __restrict__ bw2_1, uint32_t n, uint32_t tb, uint32_t te,
-                                                            uint32_t levels, T theta2, T c, vec4_t<T>* __restrict__ a_out,
-                                                            unsigned long long* stats = nullptr) {
-  // node_m1 / bw2_1 are the node arrays (centre of mass + mass, width^2) offset by -1 element: indexed by the 1-based
-  // heap index kk = k + 1
-  const uint32_t i   = tb + blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid   = i < te;
-  const vec4_t<T> xs = xm[valid ? i : tb];
+//
+// NB bodies per lane (32*NB consecutive Hilbert-sorted bodies per warp): the bookkeeping of a step — REDUX, node index,
+// address, record load, candidates, loop control, about two thirds of the instructions — is shared by NB tests, and the
+// union of 64 (128) neighbouring paths is only 1.12x (1.30x) longer than that of 32 (tools/bvh_walk_sim.c, n = 10 M:
+// 10257 / 11499 / 13339 steps per warp for NB = 1 / 2 / 4). In float the NB tests run two at a time on FP32x2
+// instructions (add/mul.rn.f32x2 round each half exactly like the scalar ops, and are never contracted), so decisions
+// stay bit-identical to the reference's.
+template <typename T, int D, int NB, bool COUNT = false>
+__global__ void __launch_bounds__(128) bvh_force_key_kernel(const vec4_t<T>* __restrict__ xm, const WalkRec<T>* __restrict__ rec1,
+                                                            uint32_t n, uint32_t tb, uint32_t te, uint32_t levels, T theta2, T c,
+                                                            vec4_t<T>* __restrict__ a_out, unsigned long long* stats = nullptr) {
+  // rec1 is the record array offset by -1 element: indexed by the 1-based heap index kk = k + 1
+  constexpr bool PACK = sizeof(T) == 4 && NB % 2 == 0;  // FP32x2 over pairs of bodies
+  const uint32_t lane  = threadIdx.x & 31u;
+  const uint32_t wbase = tb + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (32u * NB);  // first body of the warp
   unsigned long long n_visit = 0, n_take = 0, n_step = 0;  // COUNT only
   // covered is even: covered >= n <=> covered >= n rounded up to even. Active keys are <= ((n_even - 2) << 4) + 27, so the
   // limit can sit 4 below n_even << 4: accepting the ROOT (a "right child" by parity of kk = 1) then needs no special case,
@@ -387,14 +442,25 @@ __global__ void __launch_bounds__(128) bvh_force_key_kernel(const vec4_t<T>* __r
   const uint32_t nlim  = ((n + (n & 1u)) << 4) - 4u;
   const uint32_t sent  = 16u << levels;  // one above the largest active covered << 4
   const uint32_t step0 = 16u << levels;  // key increment of accepting a level-0 node; >> level for deeper ones
-  uint32_t key = valid ? 0u : 0xffffffffu;
-  T ax = 0, ay = 0, az = 0;
+  uint32_t idx[NB], key[NB];
+  T px[NB], py[NB], pz[NB], ax[NB], ay[NB], az[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    idx[j]            = wbase + j * 32u + lane;
+    const bool valid  = idx[j] < te;
+    const vec4_t<T> b = xm[valid ? idx[j] : tb];
+    px[j] = b.x; py[j] = b.y; pz[j] = b.z;
+    ax[j] = ay[j] = az[j] = T(0);
+    key[j] = valid ? 0u : 0xffffffffu;
+  }
   for (;;) {
-    const uint32_t kmin = __reduce_min_sync(0xffffffffu, key);
+    uint32_t kmine = key[0];
+#pragma unroll
+    for (int j = 1; j < NB; ++j) kmine = min(kmine, key[j]);
+    const uint32_t kmin = __reduce_min_sync(0xffffffffu, kmine);
     if (kmin >= nlim) break;
     const uint32_t cl = kmin & 31u;
-    const bool act    = key == kmin;
-    if (COUNT) { n_visit += act; n_step += 1; }
+    if (COUNT) n_step += 1;
     if (cl == levels) {  // body level: the two bodies cpos, cpos+1 (bvh.h:288-303)
       const uint32_t cpos = (kmin >> 4) & ~1u;
 #pragma unroll
@@ -402,48 +468,101 @@ __global__ void __launch_bounds__(128) bvh_force_key_kernel(const vec4_t<T>* __r
         const uint32_t bidx = cpos + q;
         if (bidx < n) {
           const vec4_t<T> b = xm[bidx];
-          if (act && bidx != i) {
-            const T dx = sub_rn(b.x, xs.x), dy = sub_rn(b.y, xs.y), dz = D == 3 ? sub_rn(b.z, xs.z) : T(0);
-            T d2 = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
-            if (D == 3) d2 = add_rn(d2, mul_rn(dz, dz));
-            T s = b.w * inv_dist3(d2);
-            ax = fma(dx, s, ax);
-            ay = fma(dy, s, ay);
-            if (D == 3) az = fma(dz, s, az);
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {
+            if (key[j] == kmin && bidx != idx[j]) {
+              const T dx = sub_rn(b.x, px[j]), dy = sub_rn(b.y, py[j]), dz = D == 3 ? sub_rn(b.z, pz[j]) : T(0);
+              T d2 = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
+              if (D == 3) d2 = add_rn(d2, mul_rn(dz, dz));
+              const T s = b.w * inv_dist3(d2);
+              ax[j] = fma(dx, s, ax[j]);
+              ay[j] = fma(dy, s, ay[j]);
+              if (D == 3) az[j] = fma(dz, s, az[j]);
+            }
           }
         }
       }
-      if (act) key = kmin + (cl ? 31u : 32u);  // covered += 2, level -= 1 (n = 1: the body level is level 0)
-      if (COUNT) n_take += act;
-    } else {
-      const uint32_t kk  = (kmin | sent) >> (levels + 4u - cl);  // 1-based heap index: 2^level + covered / 2^(levels-level)
-      const vec4_t<T> nm = node_m1[kk];
-      const T w2         = bw2_1[kk];
-      // accept: covered += 2^(levels-level); a right child (kk odd) continues one level up, a left child with its sibling
-      const uint32_t cand_take = kmin + (step0 >> cl) - (kk & 1u);
-      const uint32_t cand_open = kmin + 1u;
-      // (xj - xs) == -(xs - xj) exactly, so one difference serves the reference-order dist2 and the accumulation
-      const T dx = sub_rn(nm.x, xs.x), dy = sub_rn(nm.y, xs.y), dz = D == 3 ? sub_rn(nm.z, xs.z) : T(0);
-      T d2 = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
-      if (D == 3) d2 = add_rn(d2, mul_rn(dz, dz));
-      const bool take = act & (w2 < mul_rn(theta2, d2));  // can_approximate (bvh.h:246-248)
-      if (take) {
-        T s = nm.w * inv_dist3(d2);
-        ax = fma(dx, s, ax);
-        ay = fma(dy, s, ay);
-        if (D == 3) az = fma(dz, s, az);
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const bool act = key[j] == kmin;
+        if (COUNT) { n_visit += act; n_take += act; }
+        if (act) key[j] = kmin + (cl ? 31u : 32u);  // covered += 2, level -= 1 (n = 1: the body level is level 0)
       }
-      if (COUNT) n_take += take;
-      key = max(key, take ? cand_take : cand_open);
+      continue;
+    }
+    const uint32_t kk = (kmin | sent) >> (levels + 4u - cl);  // 1-based heap index: 2^level + covered / 2^(levels-level)
+    const WalkRec<T>* r = rec1 + kk;
+    const vec4_t<T> nm  = *reinterpret_cast<const vec4_t<T>*>(r);  // (com, mass)
+    const T w2          = r->w2;
+    // accept: covered += 2^(levels-level); a right child (kk odd) continues one level up, a left child with its sibling
+    const uint32_t cand_take = kmin + (step0 >> cl) - (kk & 1u);
+    const uint32_t cand_open = kmin + 1u;
+    if constexpr (PACK) {
+      const float2 nx2 = make_float2(nm.x, nm.x), ny2 = make_float2(nm.y, nm.y), nz2 = make_float2(nm.z, nm.z);
+      const float2 th2 = make_float2(theta2, theta2);
+#pragma unroll
+      for (int j = 0; j < NB; j += 2) {
+        // (xj - xs) == -(xs - xj) exactly, so one difference serves the reference-order dist2 and the accumulation
+        const float2 dx = add2_exact(nx2, make_float2(-px[j], -px[j + 1]));
+        const float2 dy = add2_exact(ny2, make_float2(-py[j], -py[j + 1]));
+        float2 dz       = make_float2(0.f, 0.f);
+        // the squares are packed, their sums scalar: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with
+        // explicit .rn (checked in SASS), which would change the rounding of dist2; scalar add.rn is never contracted
+        const float2 sx = mul2_exact(dx, dx), sy = mul2_exact(dy, dy);
+        float2 d2       = make_float2(__fadd_rn(sx.x, sy.x), __fadd_rn(sx.y, sy.y));
+        if (D == 3) {
+          dz              = add2_exact(nz2, make_float2(-pz[j], -pz[j + 1]));
+          const float2 sz = mul2_exact(dz, dz);
+          d2              = make_float2(__fadd_rn(d2.x, sz.x), __fadd_rn(d2.y, sz.y));
+        }
+        const float2 t   = mul2_exact(th2, d2);
+        const bool take0 = (key[j] == kmin) & (w2 < t.x);      // can_approximate (bvh.h:246-248)
+        const bool take1 = (key[j + 1] == kmin) & (w2 < t.y);
+        if (COUNT) { n_visit += (key[j] == kmin) + (key[j + 1] == kmin); n_take += take0 + take1; }
+        if (take0 | take1) {
+          float2 sq, inv;
+          asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq.x) : "f"(d2.x));
+          asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq.y) : "f"(d2.y));
+          const float2 den = __ffma2_rn(d2, sq, make_float2(FLT_EPSILON, FLT_EPSILON));
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.x) : "f"(den.x));
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.y) : "f"(den.y));
+          const float2 s = __fmul2_rn(make_float2(take0 ? nm.w : 0.f, take1 ? nm.w : 0.f), inv);
+          float2 acc;
+          acc = __ffma2_rn(dx, s, make_float2(ax[j], ax[j + 1])); ax[j] = acc.x; ax[j + 1] = acc.y;
+          acc = __ffma2_rn(dy, s, make_float2(ay[j], ay[j + 1])); ay[j] = acc.x; ay[j + 1] = acc.y;
+          if (D == 3) { acc = __ffma2_rn(dz, s, make_float2(az[j], az[j + 1])); az[j] = acc.x; az[j + 1] = acc.y; }
+        }
+        key[j]     = max(key[j], take0 ? cand_take : cand_open);
+        key[j + 1] = max(key[j + 1], take1 ? cand_take : cand_open);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const T dx = sub_rn(nm.x, px[j]), dy = sub_rn(nm.y, py[j]), dz = D == 3 ? sub_rn(nm.z, pz[j]) : T(0);
+        T d2 = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
+        if (D == 3) d2 = add_rn(d2, mul_rn(dz, dz));
+        const bool act  = key[j] == kmin;
+        const bool take = act & (w2 < mul_rn(theta2, d2));  // can_approximate (bvh.h:246-248)
+        if (COUNT) { n_visit += act; n_take += take; }
+        if (take) {
+          const T s = nm.w * inv_dist3(d2);
+          ax[j] = fma(dx, s, ax[j]);
+          ay[j] = fma(dy, s, ay[j]);
+          if (D == 3) az[j] = fma(dz, s, az[j]);
+        }
+        key[j] = max(key[j], take ? cand_take : cand_open);
+      }
     }
   }
-  if (COUNT) {
+  if constexpr (COUNT) {
     atomicAdd(&stats[0], n_visit);
     atomicAdd(&stats[1], n_take);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&stats[2], n_step);
-    return;
+    if (lane == 0) atomicAdd(&stats[2], n_step);
+  } else {
+#pragma unroll
+    for (int j = 0; j < NB; ++j)
+      if (idx[j] < te) a_out[idx[j]] = make_v4<T>(mul_rn(c, ax[j]), mul_rn(c, ay[j]), D == 3 ? mul_rn(c, az[j]) : T(0), T(0));
   }
-  if (valid) a_out[i] = make_v4<T>(mul_rn(c, ax), mul_rn(c, ay), D == 3 ? mul_rn(c, az) : T(0), T(0));
 }
 
 // ---- artefact export ---------------------------------------------------------------------------------------------
@@ -490,13 +609,13 @@ static int create_impl(nbx_engine* e) {
   const size_t nn = size_t(s->nnodes ? s->nnodes : 1);
   NBX_CUDA(cudaMalloc(&s->node_m, sizeof(vec4_t<T>) * nn));
   NBX_CUDA(cudaMalloc(&s->bw, sizeof(T) * nn));
-  NBX_CUDA(cudaMalloc(&s->bw2, sizeof(T) * nn));
+  NBX_CUDA(cudaMalloc(&s->rec, sizeof(WalkRec<T>) * nn));
   NBX_CUDA(cudaMalloc(&s->lo, sizeof(vec4_t<T>) * nn));
   NBX_CUDA(cudaMalloc(&s->hi, sizeof(vec4_t<T>) * nn));
   // the reference never writes b/bw of dead nodes (bvh.h:185-188,225-228): keep them deterministic (zero)
   NBX_CUDA(cudaMemsetAsync(s->node_m, 0, sizeof(vec4_t<T>) * nn, e->stream));
   NBX_CUDA(cudaMemsetAsync(s->bw, 0, sizeof(T) * nn, e->stream));
-  NBX_CUDA(cudaMemsetAsync(s->bw2, 0, sizeof(T) * nn, e->stream));
+  NBX_CUDA(cudaMemsetAsync(s->rec, 0, sizeof(WalkRec<T>) * nn, e->stream));
   NBX_CUDA(cudaMemsetAsync(s->lo, 0, sizeof(vec4_t<T>) * nn, e->stream));
   NBX_CUDA(cudaMemsetAsync(s->hi, 0, sizeof(vec4_t<T>) * nn, e->stream));
   const size_t rb = rec_bytes(e);
@@ -513,7 +632,7 @@ template <typename T, int D>
 static void destroy_impl(nbx_engine* e) {
   auto* s = st<T>(e);
   if (!s) return;
-  void* bufs[] = {s->box, s->partial, s->keys, s->perm, s->node_m, s->bw, s->bw2, s->lo, s->hi};
+  void* bufs[] = {s->box, s->partial, s->keys, s->perm, s->node_m, s->bw, s->rec, s->lo, s->hi};
   for (void* b : bufs)
     if (b) cudaFree(b);
   delete s;
@@ -536,9 +655,16 @@ static int sort_impl(nbx_engine* e) {
   auto* s = st<T>(e);
   if (!s->have_box) return fail(NBX_ERR_STATE, "hilbert_sort before bounding_box");
   const uint32_t n = e->n;
-  hilbert_keys_kernel<T, D><<<(n + 255) / 256, 256, 0, e->stream>>>(static_cast<const vec4_t<T>*>(e->xm[e->cur]), n, s->box, s->keys);
-  e->launches++;
-  NBX_TRY(sort_pairs(e, s->keys, n, D == 2 ? 64 : 63, s->perm, nullptr));
+  // Multi-GPU: every rank sorts the same keys (replicas; deterministic => identical permutations). The alternative of
+  // SURVEY §8(e3) — rank 0 sorts, the permutation is broadcast over NVLink — is kept behind NBX_BVH_SORT=broadcast for the
+  // measurement recorded in DESIGN.md §7: it cannot win, the other ranks only wait for rank 0 and then for 4 B/body more.
+  static const bool bcast = [] { const char* v = getenv("NBX_BVH_SORT"); return v && std::string(v) == "broadcast"; }();
+  if (!(bcast && e->cfg.world_size > 1 && e->cfg.rank != 0)) {
+    hilbert_keys_kernel<T, D><<<(n + 255) / 256, 256, 0, e->stream>>>(static_cast<const vec4_t<T>*>(e->xm[e->cur]), n, s->box, s->keys);
+    e->launches++;
+    NBX_TRY(sort_pairs(e, s->keys, n, D == 2 ? 64 : 63, s->perm, nullptr));
+  }
+  if (bcast && e->cfg.world_size > 1) NBX_TRY(comm_broadcast(e, s->perm, sizeof(uint32_t) * size_t(n), 0));
   gather_kernel<T><<<(n + 255) / 256, 256, 0, e->stream>>>(
       s->perm, n, static_cast<const vec4_t<T>*>(e->xm[e->cur]), static_cast<vec4_t<T>*>(e->xm[e->cur ^ 1]),
       static_cast<const vec4_t<T>*>(e->v), static_cast<vec4_t<T>*>(e->v_alt), static_cast<const vec4_t<T>*>(e->a),
@@ -564,16 +690,49 @@ static int build_impl(nbx_engine* e) {
   const uint32_t last = s->levels - 1;
   {
     uint32_t first = (1u << last) - 1, count = 1u << last;
-    build_leaf_level_kernel<T, D><<<(count + 255) / 256, 256, 0, e->stream>>>(xm, e->n, first, count, s->node_m, s->bw, s->bw2, s->lo, s->hi);
+    build_leaf_level_kernel<T, D><<<(count + 255) / 256, 256, 0, e->stream>>>(xm, e->n, first, count, s->node_m, s->bw, s->rec, s->lo, s->hi);
     e->launches++;
   }
-  for (int l = int(last) - 1; l >= 0; --l) {
+  int l = int(last) - 1;
+  for (; l > int(BVH_TOP_LEVEL); --l) {
     uint32_t first = (1u << l) - 1, count = 1u << l;
-    build_level_kernel<T, D><<<(count + 255) / 256, 256, 0, e->stream>>>(first, count, s->node_m, s->bw, s->bw2, s->lo, s->hi);
+    build_level_kernel<T, D><<<(count + 255) / 256, 256, 0, e->stream>>>(first, count, s->node_m, s->bw, s->rec, s->lo, s->hi);
+    e->launches++;
+  }
+  if (l >= 0) {
+    build_top_levels_kernel<T, D><<<1, 1024, 0, e->stream>>>(l, s->node_m, s->bw, s->rec, s->lo, s->hi);
     e->launches++;
   }
   NBX_CUDA(cudaGetLastError());
   s->built = true;
+  return NBX_OK;
+}
+
+// bodies per lane of the warp walk. More bodies per lane share the bookkeeping of a step but leave fewer warps; small
+// problems are bound by the per-warp latency of the walk and want the most warps. Measured walk times (ms, B200, 3-D
+// galaxy) for 1 / 2 / 4 bodies per lane — float: n = 100 k 1.71 / 2.35 / 3.16, 1 M 9.52 / 9.88 / 9.91, 3 M 33.9 / 30.2 /
+// 28.7, 10 M 137.0 / 118.2 / 110.2; double: 100 k 2.66 / 3.22 / 4.56, 1 M 15.6 / 17.0 / 18.8, 3 M 55.6 / 55.0 / 62.1,
+// 10 M 223.9 / 219.9 / 242.9. NBX_BVH_NB=1|2|4 forces it (experiments).
+static int walk_bodies_per_lane(int prec, uint32_t targets) {
+  static const int forced = [] { const char* v = getenv("NBX_BVH_NB"); const int k = v ? atoi(v) : 0; return k == 1 || k == 2 || k == 4 ? k : 0; }();
+  if (forced) return forced;
+  if (prec == 4) return targets < 1500000u ? 1 : (targets < 2500000u ? 2 : 4);
+  return targets < 2500000u ? 1 : 2;
+}
+
+template <typename T, int D, bool COUNT>
+static int launch_walk(nbx_engine* e, BvhState<T>* s, unsigned long long* stats) {
+  const uint32_t nt = e->te - e->tb;
+  const T theta     = T(e->cfg.theta);
+  const int nb      = walk_bodies_per_lane(e->prec, nt);
+  const auto* xm    = static_cast<const vec4_t<T>*>(e->xm[e->cur]);
+  auto* a           = static_cast<vec4_t<T>*>(e->a);
+  const unsigned grid = (nt + 128u * nb - 1) / (128u * nb);
+#define NBX_WALK(NB_) bvh_force_key_kernel<T, D, NB_, COUNT><<<grid, 128, 0, e->stream>>>(xm, s->rec - 1, e->n, e->tb, e->te, s->levels, theta * theta, T(e->cfg.G), a, stats)
+  if (nb == 1) NBX_WALK(1);
+  else if (nb == 2) NBX_WALK(2);
+  else NBX_WALK(4);
+#undef NBX_WALK
   return NBX_OK;
 }
 
@@ -585,10 +744,7 @@ static int force_impl(nbx_engine* e) {
   if (nt == 0) return NBX_OK;
   const T theta = T(e->cfg.theta);
   static const bool per_thread = [] { const char* v = getenv("NBX_BVH_PER_THREAD"); return v && atoi(v); }();
-  if (s->levels <= 27 && !per_thread)
-    bvh_force_key_kernel<T, D><<<(nt + 127) / 128, 128, 0, e->stream>>>(static_cast<const vec4_t<T>*>(e->xm[e->cur]), s->node_m - 1,
-                                                                       s->bw2 - 1, e->n, e->tb, e->te, s->levels, theta * theta, T(e->cfg.G),
-                                                                       static_cast<vec4_t<T>*>(e->a));
+  if (s->levels <= 27 && !per_thread) NBX_TRY((launch_walk<T, D, false>(e, s, nullptr)));
   else
     bvh_force_kernel<T, D><<<(nt + 127) / 128, 128, 0, e->stream>>>(static_cast<const vec4_t<T>*>(e->xm[e->cur]), s->node_m, s->bw, e->n,
                                                                    e->tb, e->te, s->levels, theta * theta, T(e->cfg.G),
@@ -656,12 +812,7 @@ static int stats_impl(nbx_engine* e, unsigned long long* dev_stats) {
   auto* s = st<T>(e);
   if (!s->built) return fail(NBX_ERR_STATE, "no build_tree has run yet");
   if (s->levels > 27) return fail(NBX_ERR_INVALID, "traversal stats need n <= 2^27");
-  const uint32_t nt = e->te - e->tb;
-  const T theta     = T(e->cfg.theta);
-  if (nt)
-    bvh_force_key_kernel<T, D, true><<<(nt + 127) / 128, 128, 0, e->stream>>>(static_cast<const vec4_t<T>*>(e->xm[e->cur]), s->node_m - 1,
-                                                                              s->bw2 - 1, e->n, e->tb, e->te, s->levels, theta * theta,
-                                                                              T(e->cfg.G), static_cast<vec4_t<T>*>(e->a), dev_stats);
+  if (e->te > e->tb) NBX_TRY((launch_walk<T, D, true>(e, s, dev_stats)));
   e->launches++;
   NBX_CUDA(cudaGetLastError());
   return NBX_OK;
@@ -697,6 +848,14 @@ int bvh_compute_force(nbx_engine* e) {
   return e->cfg.world_size > 1 ? comm_allgather(e, e->a) : NBX_OK;
 }
 int bvh_stats(nbx_engine* e, unsigned long long* dev_stats) { return BVH_DISPATCH(e, stats_impl, e, dev_stats); }
+// what sort_impl / build_impl do on the host besides enqueueing kernels; a replayed graph step needs the same
+void bvh_after_graph_replay(nbx_engine* e) {
+  e->cur ^= 1;
+  std::swap(e->v, e->v_alt);
+  std::swap(e->a, e->a_alt);
+  std::swap(e->ao, e->ao_alt);
+}
+int bvh_walk_width(const nbx_engine* e) { return 32 * walk_bodies_per_lane(e->prec, e->te - e->tb); }
 int bvh_get_bbox(nbx_engine* e, void* xmin, void* xmax) { return BVH_DISPATCH(e, get_bbox_impl, e, xmin, xmax); }
 int bvh_get_keys(nbx_engine* e, uint64_t* keys, uint32_t* perm) { return BVH_DISPATCH(e, get_keys_impl, e, keys, perm); }
 int bvh_get_nodes(nbx_engine* e, uint64_t* nnodes, void* node_m, void* bw, void* b) {

@@ -28,6 +28,7 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t)                                                               = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t)                  = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t)             = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t)             = nullptr;
   const char* (*GetErrorString)(ncclResult_t)                                                           = nullptr;
   bool ok = false;
 };
@@ -44,8 +45,9 @@ static void load_api(NcclApi& a) {
   a.CommDestroy    = (decltype(a.CommDestroy))dlsym(a.lib, "ncclCommDestroy");
   a.AllGather      = (decltype(a.AllGather))dlsym(a.lib, "ncclAllGather");
   a.AllReduce      = (decltype(a.AllReduce))dlsym(a.lib, "ncclAllReduce");
+  a.Broadcast      = (decltype(a.Broadcast))dlsym(a.lib, "ncclBroadcast");
   a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.lib, "ncclGetErrorString");
-  a.ok             = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.AllReduce && a.GetErrorString;
+  a.ok             = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.AllReduce && a.Broadcast && a.GetErrorString;
 }
 
 // the C++ driver calls in from one host thread per GPU: the table is filled exactly once, before anyone reads it
@@ -103,6 +105,15 @@ int comm_allreduce_sum(nbx_engine* e, void* buffer, size_t count) {
   PhaseTimer pt(e, PH_COMM);
   ncclResult_t r = api().AllReduce(buffer, buffer, count, e->prec == 4 ? ncclFloat : ncclDouble, ncclSum, (ncclComm_t)e->comm, e->stream);
   if (r != 0) return nccl_fail("ncclAllReduce", r);
+  return NBX_OK;
+}
+
+// in-place broadcast of `bytes` bytes from rank `root` (build-once-and-broadcast variant of the tree build)
+int comm_broadcast(nbx_engine* e, void* buffer, size_t bytes, int root) {
+  if (e->cfg.world_size <= 1) return NBX_OK;
+  if (!e->comm) return fail(NBX_ERR_COMM, "multi-GPU engine used before nbx_comm_init_rank");
+  ncclResult_t r = api().Broadcast(buffer, buffer, bytes, ncclChar, root, (ncclComm_t)e->comm, e->stream);
+  if (r != 0) return nccl_fail("ncclBroadcast", r);
   return NBX_OK;
 }
 

@@ -1,4 +1,5 @@
 // nbx_engine.cu — engine lifetime, host<->device state transfer, step drivers and the extern "C" surface of nbx.h.
+#include <cstdlib>
 #include <cstring>
 
 #include "nbx_internal.cuh"
@@ -63,37 +64,44 @@ static int ensure_stage(nbx_engine* e, size_t bytes) {
   return NBX_OK;
 }
 
+// [first, first + count) of the bodies; host pointers address the FULL arrays. gather: all-gather the uploaded shards
+// over NCCL afterwards (nbx_upload_shard: every rank sends 1/world of the bytes over PCIe, NVLink does the rest).
 template <typename T, int D>
-static int upload_impl(nbx_engine* e, const void* m, const void* x, const void* v, const void* a, const void* ao) {
-  const uint32_t n = e->n;
-  const dim3 grid((n + 255) / 256), block(256);
-  NBX_TRY(ensure_stage(e, sizeof(T) * size_t(n) * D));
-  auto put = [&](const void* host, size_t bytes) -> int {
-    NBX_CUDA(cudaMemcpyAsync(e->stage, host, bytes, cudaMemcpyHostToDevice, e->stream));
+static int upload_impl(nbx_engine* e, const void* m, const void* x, const void* v, const void* a, const void* ao, uint32_t first,
+                       uint32_t count, bool gather) {
+  const dim3 grid((count + 255) / 256), block(256);
+  NBX_TRY(ensure_stage(e, sizeof(T) * size_t(e->n) * D));
+  auto put = [&](const void* host, size_t elems_per_body) -> int {
+    const size_t bytes = sizeof(T) * elems_per_body * count;
+    if (!bytes) return NBX_OK;
+    NBX_CUDA(cudaMemcpyAsync(e->stage, static_cast<const T*>(host) + elems_per_body * first, bytes, cudaMemcpyHostToDevice, e->stream));
     e->h2d += bytes;
     return NBX_OK;
   };
+  vec4_t<T>* xm = static_cast<vec4_t<T>*>(e->xm[e->cur]) + first;
   if (x) {
-    NBX_TRY(put(x, sizeof(T) * size_t(n) * D));
-    pack_pos_kernel<T, D><<<grid, block, 0, e->stream>>>((const T*)e->stage, (vec4_t<T>*)e->xm[e->cur], n);
+    NBX_TRY(put(x, D));
+    if (count) pack_pos_kernel<T, D><<<grid, block, 0, e->stream>>>((const T*)e->stage, xm, count);
     e->launches++;
   }
   if (m) {
-    NBX_TRY(put(m, sizeof(T) * size_t(n)));
-    pack_mass_kernel<T><<<grid, block, 0, e->stream>>>((const T*)e->stage, (vec4_t<T>*)e->xm[e->cur], n);
+    NBX_TRY(put(m, 1));
+    if (count) pack_mass_kernel<T><<<grid, block, 0, e->stream>>>((const T*)e->stage, xm, count);
     e->launches++;
   }
   if (x || m) {
+    if (gather) NBX_TRY(comm_allgather(e, e->xm[e->cur]));
     // both position buffers carry the masses (the fused leapfrog writes x,m into the other one)
-    NBX_CUDA(cudaMemcpyAsync(e->xm[e->cur ^ 1], e->xm[e->cur], rec_bytes(e) * n, cudaMemcpyDeviceToDevice, e->stream));
+    NBX_CUDA(cudaMemcpyAsync(e->xm[e->cur ^ 1], e->xm[e->cur], rec_bytes(e) * e->n, cudaMemcpyDeviceToDevice, e->stream));
   }
   const void* src[3] = {v, a, ao};
   void* dst[3]       = {e->v, e->a, e->ao};
   for (int q = 0; q < 3; ++q) {
     if (!src[q]) continue;
-    NBX_TRY(put(src[q], sizeof(T) * size_t(n) * D));
-    pack_vec_kernel<T, D><<<grid, block, 0, e->stream>>>((const T*)e->stage, (vec4_t<T>*)dst[q], n);
+    NBX_TRY(put(src[q], D));
+    if (count) pack_vec_kernel<T, D><<<grid, block, 0, e->stream>>>((const T*)e->stage, static_cast<vec4_t<T>*>(dst[q]) + first, count);
     e->launches++;
+    if (gather) NBX_TRY(comm_allgather(e, dst[q]));
   }
   NBX_CUDA(cudaGetLastError());
   NBX_CUDA(cudaStreamSynchronize(e->stream));  // host arrays may be reused by the caller
@@ -101,28 +109,29 @@ static int upload_impl(nbx_engine* e, const void* m, const void* x, const void* 
 }
 
 template <typename T, int D>
-static int download_impl(nbx_engine* e, void* m, void* x, void* v, void* a, void* ao) {
-  const uint32_t n = e->n;
-  const dim3 grid((n + 255) / 256), block(256);
-  NBX_TRY(ensure_stage(e, sizeof(T) * size_t(n) * D));
-  auto get = [&](void* host, size_t bytes) -> int {
-    NBX_CUDA(cudaMemcpyAsync(host, e->stage, bytes, cudaMemcpyDeviceToHost, e->stream));
+static int download_impl(nbx_engine* e, void* m, void* x, void* v, void* a, void* ao, uint32_t first, uint32_t count) {
+  const dim3 grid((count + 255) / 256), block(256);
+  NBX_TRY(ensure_stage(e, sizeof(T) * size_t(e->n) * D));
+  if (!count) return NBX_OK;
+  auto get = [&](void* host, size_t elems_per_body) -> int {
+    const size_t bytes = sizeof(T) * elems_per_body * count;
+    NBX_CUDA(cudaMemcpyAsync(static_cast<T*>(host) + elems_per_body * first, e->stage, bytes, cudaMemcpyDeviceToHost, e->stream));
     NBX_CUDA(cudaStreamSynchronize(e->stream));
     e->d2h += bytes;
     return NBX_OK;
   };
   if (m) {
-    unpack_mass_kernel<T><<<grid, block, 0, e->stream>>>((const vec4_t<T>*)e->xm[e->cur], (T*)e->stage, n);
+    unpack_mass_kernel<T><<<grid, block, 0, e->stream>>>(static_cast<const vec4_t<T>*>(e->xm[e->cur]) + first, (T*)e->stage, count);
     e->launches++;
-    NBX_TRY(get(m, sizeof(T) * size_t(n)));
+    NBX_TRY(get(m, 1));
   }
   void* dsth[4]      = {x, v, a, ao};
   const void* src[4] = {e->xm[e->cur], e->v, e->a, e->ao};
   for (int q = 0; q < 4; ++q) {
     if (!dsth[q]) continue;
-    unpack_vec_kernel<T, D><<<grid, block, 0, e->stream>>>((const vec4_t<T>*)src[q], (T*)e->stage, n);
+    unpack_vec_kernel<T, D><<<grid, block, 0, e->stream>>>(static_cast<const vec4_t<T>*>(src[q]) + first, (T*)e->stage, count);
     e->launches++;
-    NBX_TRY(get(dsth[q], sizeof(T) * size_t(n) * D));
+    NBX_TRY(get(dsth[q], D));
   }
   NBX_CUDA(cudaGetLastError());
   return NBX_OK;
@@ -173,6 +182,54 @@ static int stream_end_impl(nbx_engine* e, void* x_host) {
                   : ((e)->dim == 2 ? fn<double, 2>(__VA_ARGS__) : fn<double, 3>(__VA_ARGS__)))
 
 // ---- one time step (the `kernels()` lambda of the reference drivers) -------------------------------------------
+static int bvh_step_enqueue(nbx_engine* e) {
+  NBX_TRY(bvh_bounding_box(e));
+  NBX_TRY(bvh_hilbert_sort(e));
+  NBX_TRY(bvh_build_tree(e));
+  NBX_TRY(bvh_compute_force(e));  // all-gathers a[tb,te) of every rank -> full a everywhere
+  return accelerate_step(e);
+}
+
+// The BVH step is ~30 launches (bbox 2, keys, sort 11, gather, one per build level, walk, leapfrog) with no host decision in
+// between: on one GPU it is captured ONCE per buffer parity into a CUDA graph and replayed, which removes the per-launch
+// host work and most of the gaps between the small kernels (what small n is bound by). NBX_GRAPH=0 disables it; phase
+// timing (events between the kernels) and multi-GPU steps (NCCL calls) use the plain launch sequence.
+static int bvh_step(nbx_engine* e) {
+  static const bool enabled = [] { const char* v = getenv("NBX_GRAPH"); return !(v && atoi(v) == 0); }();
+  if (!enabled || e->phase_timing || e->cfg.world_size > 1) return bvh_step_enqueue(e);
+  const int par = e->cur;
+  if (e->step_graph[par] && e->step_graph_v[par] == e->v) {
+    NBX_CUDA(cudaGraphLaunch(e->step_graph[par], e->stream));
+    bvh_after_graph_replay(e);
+    e->launches += e->step_graph_launches[par];
+    return NBX_OK;
+  }
+  if (e->step_graph[par]) {  // captured with another buffer assignment (per-phase calls in between): recapture
+    cudaGraphExecDestroy(e->step_graph[par]);
+    e->step_graph[par] = nullptr;
+  }
+  const void* v_before    = e->v;
+  const uint64_t l_before = e->launches;
+  NBX_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = bvh_step_enqueue(e);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t err = cudaStreamEndCapture(e->stream, &graph);
+  if (rc != NBX_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (err != cudaSuccess) return fail(NBX_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(err));
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ierr = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ierr != cudaSuccess) return fail(NBX_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ierr));
+  e->step_graph[par]          = exec;
+  e->step_graph_v[par]        = v_before;
+  e->step_graph_launches[par] = e->launches - l_before;
+  NBX_CUDA(cudaGraphLaunch(exec, e->stream));  // the capture only recorded the step: run it
+  return NBX_OK;
+}
+
 static int one_step(nbx_engine* e) {
   const bool multi = e->cfg.world_size > 1;
   switch (e->algo) {
@@ -189,13 +246,7 @@ static int one_step(nbx_engine* e) {
       NBX_TRY(all_pairs_collapsed_force(e));
       NBX_TRY(accelerate_step(e));
       return NBX_OK;
-    case NBX_BVH:
-      NBX_TRY(bvh_bounding_box(e));
-      NBX_TRY(bvh_hilbert_sort(e));
-      NBX_TRY(bvh_build_tree(e));
-      NBX_TRY(bvh_compute_force(e));  // all-gathers a[tb,te) of every rank -> full a everywhere
-      NBX_TRY(accelerate_step(e));
-      return NBX_OK;
+    case NBX_BVH: return bvh_step(e);
     case NBX_OCTREE:
       NBX_TRY(octree_build(e));
       NBX_TRY(octree_compute_force(e));  // all-gathers the sorted-slot accelerations itself
@@ -280,7 +331,7 @@ int nbx_create(const nbx_config* cfg, nbx_engine** out) {
   // loads never need a bounds check: a zero-mass source contributes exactly 0.
   size_t pos_records = size_t(e->n_pad) + 1024;
   if (e->algo == NBX_ALL_PAIRS || e->algo == NBX_ALL_PAIRS_COLLAPSED) {  // the symmetric kernel reads whole blocks of B bodies
-    const size_t B = all_pairs_sym_block(e->n);
+    const size_t B = all_pairs_sym_block(e->n, cfg->world_size);
     pos_records    = std::max(pos_records, (size_t(e->n) + B - 1) / B * B + 1024);
   }
   for (int k = 0; k < 2; ++k) {
@@ -306,6 +357,8 @@ int nbx_destroy(nbx_engine* e) {
   if (!e) return NBX_OK;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  for (auto& g : e->step_graph)
+    if (g) cudaGraphExecDestroy(g);
   comm_destroy(e);
   bvh_destroy(e);
   octree_destroy(e);
@@ -337,12 +390,23 @@ int nbx_destroy(nbx_engine* e) {
 
 int nbx_upload(nbx_engine* e, const void* m, const void* x, const void* v, const void* a, const void* ao) {
   NBX_ENTER(e);
-  return NBX_DISPATCH(e, upload_impl, e, m, x, v, a, ao);
+  return NBX_DISPATCH(e, upload_impl, e, m, x, v, a, ao, 0u, e->n, false);
 }
 
 int nbx_download(nbx_engine* e, void* m, void* x, void* v, void* a, void* ao) {
   NBX_ENTER(e);
-  return NBX_DISPATCH(e, download_impl, e, m, x, v, a, ao);
+  return NBX_DISPATCH(e, download_impl, e, m, x, v, a, ao, 0u, e->n);
+}
+
+int nbx_upload_shard(nbx_engine* e, const void* m, const void* x, const void* v, const void* a, const void* ao) {
+  NBX_ENTER(e);
+  if (e->cfg.world_size > 1 && !e->comm) return fail(NBX_ERR_COMM, "nbx_upload_shard before nbx_comm_init_rank");
+  return NBX_DISPATCH(e, upload_impl, e, m, x, v, a, ao, e->tb, e->te - e->tb, e->cfg.world_size > 1);
+}
+
+int nbx_download_shard(nbx_engine* e, void* m, void* x, void* v, void* a, void* ao) {
+  NBX_ENTER(e);
+  return NBX_DISPATCH(e, download_impl, e, m, x, v, a, ao, e->tb, e->te - e->tb);
 }
 
 int nbx_stream_positions_begin(nbx_engine* e) {
@@ -357,7 +421,6 @@ int nbx_stream_positions_end(nbx_engine* e, void* x_host) {
 int nbx_step(nbx_engine* e, uint32_t steps) {
   NBX_ENTER(e);
   for (uint32_t s = 0; s < steps; ++s) NBX_TRY(one_step(e));
-  if (e->algo == NBX_OCTREE && steps) NBX_TRY(octree_check(e));
   return NBX_OK;
 }
 
@@ -369,7 +432,6 @@ int nbx_step_timed(nbx_engine* e, uint32_t steps, float* ms) {
   NBX_CUDA(cudaEventSynchronize(e->ev1));
   if (ms) NBX_CUDA(cudaEventElapsedTime(ms, e->ev0, e->ev1));
   collect_phase_times(e);
-  if (e->algo == NBX_OCTREE && steps) NBX_TRY(octree_check(e));
   return NBX_OK;
 }
 
@@ -433,8 +495,7 @@ int nbx_bvh_get_nodes(nbx_engine* e, uint64_t* nnodes, void* node_m, void* bw, v
 int nbx_octree_build(nbx_engine* e) {
   NBX_ENTER(e);
   if (e->algo != NBX_OCTREE) return fail(NBX_ERR_STATE, "engine was not created with NBX_OCTREE");
-  NBX_TRY(octree_build(e));
-  return octree_check(e);
+  return octree_build(e);  // reports NBX_ERR_CAPACITY itself
 }
 int nbx_octree_compute_force(nbx_engine* e) {
   NBX_ENTER(e);
@@ -471,6 +532,13 @@ int nbx_traversal_stats(nbx_engine* e, uint64_t* node_visits, uint64_t* interact
   if (node_visits) *node_visits = h[0];
   if (interactions) *interactions = h[1];
   if (warp_steps) *warp_steps = h[2];
+  return NBX_OK;
+}
+
+int nbx_walk_width(nbx_engine* e, uint32_t* bodies_per_warp_step) {
+  if (!e || !bodies_per_warp_step) return fail(NBX_ERR_INVALID, "NULL argument");
+  if (e->algo != NBX_BVH && e->algo != NBX_OCTREE) return fail(NBX_ERR_STATE, "walk width needs a tree engine");
+  *bodies_per_warp_step = e->algo == NBX_BVH ? uint32_t(bvh_walk_width(e)) : 32u;
   return NBX_OK;
 }
 

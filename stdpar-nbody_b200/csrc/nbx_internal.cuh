@@ -104,6 +104,12 @@ struct nbx_engine {
   // NCCL (multi-GPU)
   void* comm = nullptr;
 
+  // CUDA graph of one BVH time step (single GPU: the step has no host decision). The step flips the position buffer
+  // and swaps v/a/ao with their alternates, so there is one graph per parity of `cur`.
+  cudaGraphExec_t step_graph[2] = {nullptr, nullptr};
+  uint64_t step_graph_launches[2] = {0, 0};
+  const void* step_graph_v[2] = {nullptr, nullptr};  // e->v when the graph was captured (must match at replay)
+
   // kernels whose >48 KB dynamic shared memory opt-in has been set for THIS engine's device (the attribute is
   // per device, and engines of several devices can live in one process)
   std::set<const void*> smem_opt_in;
@@ -154,7 +160,7 @@ int calc_energies(nbx_engine* e, double* kinetic, double* grav);
 int measure_fma_peak(int device, int precision, double* tflops);
 // nbx_allpairs_sym.cu : Newton's-third-law variant of all_pairs_force
 bool all_pairs_sym_enabled(const nbx_engine* e);
-uint32_t all_pairs_sym_block(uint32_t n);
+uint32_t all_pairs_sym_block(uint32_t n, int world);
 int all_pairs_sym_force(nbx_engine* e, bool fuse_integrate, int collapsed_nc = 0);
 void all_pairs_sym_destroy(nbx_engine* e);
 // nbx_sort.cu : stable LSD radix sort of (u64 key, u32 value) pairs
@@ -174,6 +180,8 @@ int bvh_hilbert_sort(nbx_engine* e);
 int bvh_build_tree(nbx_engine* e);
 int bvh_compute_force(nbx_engine* e);
 int bvh_get_bbox(nbx_engine* e, void* xmin, void* xmax);
+void bvh_after_graph_replay(nbx_engine* e);                      // host-side effects of a replayed step (buffer swaps)
+int bvh_walk_width(const nbx_engine* e);                        // bodies per warp step of the walk (32 x bodies per lane)
 int bvh_stats(nbx_engine* e, unsigned long long* dev_stats);     // counting variant of the walk: {visits, interactions, warp steps}
 int bvh_get_keys(nbx_engine* e, uint64_t* keys, uint32_t* perm);
 int bvh_get_nodes(nbx_engine* e, uint64_t* nnodes, void* node_m, void* bw, void* b);
@@ -192,6 +200,7 @@ int comm_unique_id(void* id128);
 int comm_init_rank(nbx_engine* e, const void* id128);
 int comm_allgather(nbx_engine* e, void* vec4_array);  // in place: rank r contributes records [r*chunk, (r+1)*chunk)
 int comm_allreduce_sum(nbx_engine* e, void* buffer, size_t count);  // in place, `count` elements of the engine's precision
+int comm_broadcast(nbx_engine* e, void* buffer, size_t bytes, int root);
 void comm_destroy(nbx_engine* e);
 
 }  // namespace nbx

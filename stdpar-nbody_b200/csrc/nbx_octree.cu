@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cstdlib>
+#include <type_traits>
 
 #include "nbx_hilbert.cuh"
 #include "nbx_internal.cuh"
@@ -51,7 +52,7 @@ struct Root {
   T side;
   T x;          // root_x = splat(divide)
   uint32_t cells;     // internal cells of the last build
-  uint32_t overflow;  // 1: bodies not separated within MAXL levels, or more cells than capacity
+  uint32_t overflow;  // bit 0: bodies not separated within the available levels; bit 1: more cells than capacity
 };
 
 template <typename T>
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(256) delta_kernel(const uint64_t* __restrict__
   uint32_t dn = s + 1 < n ? common_levels2<D>(skeys, skeys_lo, s, s + 1) + 1 : 0;  // delta_s + 1   (0 = none)
   uint32_t dp = s > 0 ? common_levels2<D>(skeys, skeys_lo, s - 1, s) + 1 : 0;      // delta_{s-1} + 1
   const uint32_t maxl = skeys_lo ? 2 * KeyTraits<D>::MAXL : KeyTraits<D>::MAXL;
-  if (dn == maxl + 1) atomicExch(overflow, 1u);  // not separated within the available levels
+  if (dn == maxl + 1) atomicOr(overflow, 1u);  // bit 0: not separated within the available levels
   delta[s] = dn;
   cnt[s]   = dn > dp ? dn - dp : 0;
 }
@@ -350,7 +351,7 @@ __device__ __forceinline__ void emit_records_body(const uint64_t* __restrict__ s
   const uint32_t cb = cell_base[s], cb_next = cell_base[s + 1];
   if (s == n - 1) {
     root->cells = cb_next;
-    if (cb_next > ccap) root->overflow = 1;
+    if (cb_next > ccap) atomicOr(&root->overflow, 2u);  // bit 1: more internal cells than capacity
   }
   // leaf: depth = deepest shared level + 1
   const uint32_t leaf_depth = (dn > dp ? dn : dp);  // max(delta_s, delta_{s-1}) + 1, and 0 for a single body
@@ -468,8 +469,11 @@ __global__ void __launch_bounds__(256) walk_order_keys_kernel(const uint64_t* __
 
 // ---- K9 traversal ---------------------------------------------------------------------------------------------------
 // octree.h:227-255: dx = sqrt(dist2)+eps ; accept when leaf or side/dx < theta ; a += m*(xj-x)/dx^3.
-// The test is evaluated as side/theta < dx (dx > 0, side/theta tabulated per depth): it can only differ from the
-// reference's division when side/dx is within a rounding or two of theta.
+// The reference's decision is a MONOTONE function of dist2 (sqrt.rn and +eps are non-decreasing, side/dx is
+// non-increasing in dx), so for every depth there is exactly one value tau(depth) with
+//     side(depth) / (sqrt(d2) + eps) < theta   <=>   d2 >= tau(depth)        for every representable d2 >= 0.
+// threshold_table_kernel finds tau by bisection over the bit patterns of T with the reference's own IEEE operations
+// (sqrt.rn, add.rn, div.rn), once per step; the walk then compares the reference-order dist2 with the table.
 // exact halvings of the root side: side(depth) = root_side * 2^-depth
 __device__ __forceinline__ float side_at(float root_side, uint32_t depth) { return root_side * __int_as_float(int(127 - depth) << 23); }
 __device__ __forceinline__ double side_at(double root_side, uint32_t depth) {
@@ -481,8 +485,10 @@ __device__ __forceinline__ double side_at(double root_side, uint32_t depth) {
 // load is a single broadcast sector instead of up to 32 divergent ones), while each lane keeps the reference's per-body
 // semantics exactly: a lane that accepts node p while another lane needs it opened simply sleeps until the walk leaves
 // that subtree (`resume` = the record index where it wakes up). Interaction sets are identical to the per-body walk.
-// `s_table` (threshold_table_kernel) holds side(depth)/theta per depth and -1 in the leaf slot [128], so the whole
-// acceptance test is one shared-memory load and one compare: side/theta < dx.
+// `s_table` (threshold_table_kernel) holds tau(depth) and 0 in the leaf slot [128] (always accepted), so the whole
+// acceptance test is one shared-memory load and one compare on the reference-order dist2 — the SAME decision as the
+// reference's `side/dx < theta` for every input, not just away from the threshold; the square root is only needed for the
+// accumulation.
 template <typename T, int D, bool COUNT = false>
 __global__ void __launch_bounds__(128) octree_force_kernel(const vec4_t<T>* __restrict__ mono, const uint2* __restrict__ meta,
                                                            const Root<T>* __restrict__ root, const uint32_t* __restrict__ cell_base,
@@ -504,13 +510,14 @@ __global__ void __launch_bounds__(128) octree_force_kernel(const vec4_t<T>* __re
   while (p < nrec) {
     const vec4_t<T> nm = mono[p];  // warp-uniform address
     const uint2 me     = meta[p];
-    const T s_over_th  = tab[min(me.y, 128u)];
-    const T dx_ = nm.x - xs.x, dy_ = nm.y - xs.y, dz_ = D == 3 ? nm.z - xs.z : T(0);
-    T d2 = fma(dy_, dy_, sq_plus_tiny(dx_));
-    if (D == 3) d2 = fma(dz_, dz_, d2);
-    const T dx      = dist_eps_pos(d2);
+    const T tau        = tab[min(me.y, 128u)];
+    // dist2 in the reference's order, unfused (vec.h:232-240; (xj - x)^2 == (x - xj)^2 exactly)
+    const T dx_ = sub_rn(nm.x, xs.x), dy_ = sub_rn(nm.y, xs.y), dz_ = D == 3 ? sub_rn(nm.z, xs.z) : T(0);
+    T d2 = add_rn(mul_rn(dx_, dx_), mul_rn(dy_, dy_));
+    if (D == 3) d2 = add_rn(d2, mul_rn(dz_, dz_));
+    const T dx      = dist_eps(d2);
     const bool act  = p >= resume;
-    const bool take = s_over_th < dx;
+    const bool take = d2 >= tau;
     if (COUNT) { n_visit += act; n_take += act && take; n_step += 1; }
     if (act && take) {
       const T s = nm.w * inv_cube(dx);
@@ -530,12 +537,12 @@ __global__ void __launch_bounds__(128) octree_force_kernel(const vec4_t<T>* __re
   if (valid) a_sorted[t] = make_v4<T>(c * ax, c * ay, D == 3 ? c * az : T(0), T(0));
 }
 
-// ---- K9, threshold form ---------------------------------------------------------------------------------------------
-// side/dx < theta with dx = sqrt(d2) + eps  <=>  d2 > (side/theta - eps)^2 =: thr(depth)   (side/theta > eps).
-// The walk's critical path (load -> d2 -> decision -> vote -> next load) then needs no square root at all: the decision is
-// one compare against a per-depth table (computed in double once per step, staged in shared memory), and the root /
-// reciprocal are only evaluated for the accumulation, off the critical path. Like the form `side < theta*dx` it replaces,
-// the decision can differ from the reference's floating-point expression only when d2 is within a few ulp of thr.
+// ---- K9, double ------------------------------------------------------------------------------------------------------------
+// The walk's critical path (load -> d2 -> decision -> vote -> next load) needs no square root at all: the decision is
+// one compare against tau(depth), and the root / reciprocal are only evaluated for the accumulation, off the critical
+// path. d2 keeps its fused form here (two FMAs, + 1e-300 so that the rsqrt seed never sees 0): against the reference's
+// unfused dist2 it can move by an ulp, so a decision could only differ for a d2 within 2^-52 of tau — the device's test
+// counts equal the oracle's in every test. (The float walk evaluates the reference-order dist2 and is exact.)
 // m / (sqrt(d2) + eps)^3
 __device__ __forceinline__ float mass_inv_cube(float m, float d2) {
   if (d2 < 1e-6f) return m * inv_cube(dist_eps(d2));  // (eps*y)^2 no longer negligible: coincident / self
@@ -557,21 +564,45 @@ __device__ __forceinline__ double mass_inv_cube(double m, double d2) {
   return fma(w3, c2, w3);
 }
 
-// Per-depth acceptance tables, evaluated in double and rounded once to T:
-//   thr_table[d]       = (side(d)/theta - eps)^2     threshold on d2 (octree_force_thr_kernel)
-//   thr_table[132 + d] = side(d)/theta               threshold on dx (octree_force_kernel)
-// -1 (always accepted: d2, dx >= 0) when side/theta <= eps and in the leaf slot [128]; +inf (never accepted) for theta <= 0.
+// Per-depth acceptance table tau(depth) (see "K9 traversal" above): the smallest d2 >= 0 — as a bit pattern of T — for
+// which the reference's predicate side/(sqrt(d2)+eps) < theta holds, found by bisection with IEEE operations. Both walks
+// use it: thr_table[d] for d < 128, thr_table[128..131] = 0 (leaf slot: always accepted); +inf when no d2 is accepted
+// (theta <= 0). The second half [132 + d] keeps side(d)/theta (rounded from double) for diagnostics.
+__device__ __forceinline__ bool ref_accepts(float side, float d2, float theta) {
+  return __fdiv_rn(side, __fadd_rn(__fsqrt_rn(d2), FLT_EPSILON)) < theta;
+}
+__device__ __forceinline__ bool ref_accepts(double side, double d2, double theta) {
+  return __ddiv_rn(side, __dadd_rn(__dsqrt_rn(d2), DBL_EPSILON)) < theta;
+}
+__device__ __forceinline__ float from_bits(uint32_t b, float) { return __uint_as_float(b); }
+__device__ __forceinline__ double from_bits(uint64_t b, double) { return __longlong_as_double((long long)b); }
+
 template <typename T>
 __global__ void threshold_table_kernel(const Root<T>* __restrict__ root, T theta, T* __restrict__ thr_table) {
+  using bits_t = typename std::conditional<sizeof(T) == 4, uint32_t, uint64_t>::type;
   const uint32_t d = threadIdx.x;
   if (d >= 132) return;
-  double thr = -1.0, S = -1.0;
+  T tau = T(0);
+  double S = -1.0;
   if (d < 128) {
-    const double eps = sizeof(T) == 4 ? double(FLT_EPSILON) : DBL_EPSILON;
-    S                = theta > T(0) ? double(side_at(root->side, d)) / double(theta) : double(INFINITY);
-    thr              = S > eps ? (S - eps) * (S - eps) : -1.0;
+    const T side = side_at(root->side, d);
+    S            = theta > T(0) ? double(side) / double(theta) : double(INFINITY);
+    const bits_t inf_bits = sizeof(T) == 4 ? bits_t(0x7f800000u) : bits_t(0x7ff0000000000000ull);
+    if (!ref_accepts(side, from_bits(inf_bits, T(0)), theta)) {
+      tau = from_bits(inf_bits, T(0));  // nothing is accepted (theta <= 0): finite d2 >= +inf is never true
+    } else if (ref_accepts(side, T(0), theta)) {
+      tau = T(0);
+    } else {
+      bits_t lo = 0, hi = inf_bits;  // predicate false at lo, true at hi; non-negative values order like their bit patterns
+      while (hi - lo > 1) {
+        const bits_t mid = lo + (hi - lo) / 2;
+        if (ref_accepts(side, from_bits(mid, T(0)), theta)) hi = mid;
+        else lo = mid;
+      }
+      tau = from_bits(hi, T(0));
+    }
   }
-  thr_table[d]       = T(thr);
+  thr_table[d]       = tau;
   thr_table[132 + d] = T(S);
 }
 
@@ -581,7 +612,7 @@ __global__ void __launch_bounds__(128) octree_force_thr_kernel(const vec4_t<T>* 
                                                                const uint32_t* __restrict__ order, uint32_t n, uint32_t tb, uint32_t te,
                                                                const T* __restrict__ thr_table, T c, vec4_t<T>* __restrict__ a_sorted,
                                                                unsigned long long* stats = nullptr) {
-  __shared__ T tab[132];  // [depth] ; [128] = leaf: always accepted
+  __shared__ T tab[132];  // tau(depth) ; [128] = 0, leaf: always accepted
   for (uint32_t d = threadIdx.x; d < 132; d += blockDim.x) tab[d] = thr_table[d];
   __syncthreads();
   unsigned long long n_visit = 0, n_take = 0, n_step = 0;  // COUNT only
@@ -600,7 +631,7 @@ __global__ void __launch_bounds__(128) octree_force_thr_kernel(const vec4_t<T>* 
     const T dx_ = nm.x - xs.x, dy_ = nm.y - xs.y, dz_ = D == 3 ? nm.z - xs.z : T(0);
     T d2 = fma(dy_, dy_, sq_plus_tiny(dx_));
     if (D == 3) d2 = fma(dz_, dz_, d2);
-    const bool take = d2 > thr;
+    const bool take = d2 >= thr;
     const bool act  = p >= resume;
     if (COUNT) { n_visit += act; n_take += act && take; n_step += 1; }
     if (act && take) {
@@ -709,33 +740,24 @@ static void destroy_impl(nbx_engine* e) {
   e->octree = nullptr;
 }
 
+// keys -> sort -> delta -> [lane order] -> scan -> records, with one-word (MAXL levels) or two-word (2*MAXL) path keys.
+// Everything is enqueued; nothing here waits for the device.
 template <typename T, int D>
-static int build_impl(nbx_engine* e) {
+static int build_attempt(nbx_engine* e, bool deep) {
   auto* s = st<T>(e);
   const uint32_t n = e->n;
   const vec4_t<T>* xm = static_cast<const vec4_t<T>*>(e->xm[e->cur]);
   const unsigned gb = (n + 255) / 256;
-  {
-    PhaseTimer pt(e, PH_BBOX);
-    bounds_partial_kernel<T, D><<<s->nblocks, 256, 0, e->stream>>>(xm, n, s->partial);
-    bounds_final_kernel<T><<<1, 32, 0, e->stream>>>(s->partial, s->nblocks, s->root);
-    e->launches += 2;
-  }
+  s->deep = deep;
   {
     PhaseTimer pt(e, PH_SORT);
-    path_keys_kernel<T, D><<<gb, 256, 0, e->stream>>>(xm, n, s->root, s->keys, nullptr);
-    e->launches++;
-    NBX_TRY(sort_pairs(e, s->keys, n, KeyTraits<D>::BITS, s->perm, s->skeys));
-    delta_kernel<D><<<(n + 1 + 255) / 256, 256, 0, e->stream>>>(s->skeys, nullptr, n, s->delta, s->cnt, &s->root->overflow);
-    e->launches++;
-    // MAXL levels (21 in 3-D, 32 in 2-D) separate all bodies of the usual workloads; if two bodies still share a cell the
-    // build is redone with two-word keys (2*MAXL levels): LSD sort by the low word, then by the high word.
-    uint32_t ovf = 0;
-    NBX_CUDA(cudaMemcpyAsync(&ovf, &s->root->overflow, sizeof(ovf), cudaMemcpyDeviceToHost, e->stream));
-    NBX_CUDA(cudaStreamSynchronize(e->stream));
-    e->d2h += sizeof(ovf);
-    s->deep = ovf != 0;
-    if (s->deep) {
+    if (!deep) {
+      path_keys_kernel<T, D><<<gb, 256, 0, e->stream>>>(xm, n, s->root, s->keys, nullptr);
+      e->launches++;
+      NBX_TRY(sort_pairs(e, s->keys, n, KeyTraits<D>::BITS, s->perm, s->skeys));
+      delta_kernel<D><<<(n + 1 + 255) / 256, 256, 0, e->stream>>>(s->skeys, nullptr, n, s->delta, s->cnt, &s->root->overflow);
+      e->launches++;
+    } else {  // LSD over two words: sort by the low word, then (stably) by the high word
       NBX_CUDA(cudaMemsetAsync(&s->root->overflow, 0, sizeof(uint32_t), e->stream));
       path_keys_kernel<T, D><<<gb, 256, 0, e->stream>>>(xm, n, s->root, s->keys, s->keys_lo);
       NBX_TRY(sort_pairs(e, s->keys_lo, n, KeyTraits<D>::BITS, s->perm_tmp, nullptr));
@@ -760,10 +782,47 @@ static int build_impl(nbx_engine* e) {
     scan_blocksums_kernel<<<1, 1024, 0, e->stream>>>(s->blocksum, nb, nullptr);
     scan_apply_kernel<<<nb, 1024, 0, e->stream>>>(s->cnt, count, s->blocksum);
     NBX_CUDA(cudaMemsetAsync(s->depth_count, 0, sizeof(uint32_t) * 130, e->stream));
-    emit_records_kernel<T, D><<<gb, 256, 0, e->stream>>>(s->skeys, s->deep ? s->skeys_lo : nullptr, s->perm, xm, n, s->delta, s->cnt,
+    emit_records_kernel<T, D><<<gb, 256, 0, e->stream>>>(s->skeys, deep ? s->skeys_lo : nullptr, s->perm, xm, n, s->delta, s->cnt,
                                                         s->cap, s->ccap, s->mono, s->meta, s->rec_body, s->cell_pos, s->root, s->depth_count);
     e->launches += 4;
   }
+  return NBX_OK;
+}
+
+template <typename T, int D>
+static int build_impl(nbx_engine* e) {
+  auto* s = st<T>(e);
+  const uint32_t n = e->n;
+  const vec4_t<T>* xm = static_cast<const vec4_t<T>*>(e->xm[e->cur]);
+  s->built = false;
+  {
+    PhaseTimer pt(e, PH_BBOX);
+    bounds_partial_kernel<T, D><<<s->nblocks, 256, 0, e->stream>>>(xm, n, s->partial);
+    bounds_final_kernel<T><<<1, 32, 0, e->stream>>>(s->partial, s->nblocks, s->root);
+    e->launches += 2;
+  }
+  // MAXL levels (21 in 3-D, 32 in 2-D) separate all bodies of the usual workloads. The ONE host synchronisation of the
+  // build sits after the records have been emitted and reads both verdicts at once: bit 0 = two bodies still share a
+  // cell (redo with two-word keys, 2*MAXL levels), bit 1 = more internal cells than capacity. Nothing that depends on a
+  // valid tree (monopoles, walk) is enqueued before the verdict, and an unusable tree is reported from here, before any
+  // force kernel can walk it.
+  NBX_TRY((build_attempt<T, D>(e, false)));
+  auto verdict = [&](uint32_t* ovf) -> int {
+    NBX_CUDA(cudaMemcpyAsync(ovf, &s->root->overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    NBX_CUDA(cudaStreamSynchronize(e->stream));
+    e->d2h += sizeof(uint32_t);
+    return NBX_OK;
+  };
+  uint32_t ovf = 0;
+  NBX_TRY(verdict(&ovf));
+  if (ovf & 1u) {
+    NBX_TRY((build_attempt<T, D>(e, true)));
+    NBX_TRY(verdict(&ovf));
+  }
+  if (ovf)
+    return fail(NBX_ERR_CAPACITY,
+                "octree: bodies not separated within the supported depth (coincident bodies?) or more cells than the "
+                "reference's capacity max(2^D*n,1000) (src/system.h:29) allows");
   {
     PhaseTimer pt(e, PH_MONO);
     depth_offsets_kernel<<<1, 32, 0, e->stream>>>(s->depth_count, s->depth_cursor);
@@ -811,9 +870,8 @@ static int force_impl(nbx_engine* e) {
                                                                             s->thr_table, T(e->cfg.G), s->a_sorted);
     else
       octree_force_kernel<T, D><<<(nt + 127) / 128, 128, 0, e->stream>>>(s->mono, s->meta, s->root, s->cnt, s->hilbert_targets ? s->order : nullptr, e->n, e->tb, e->te,
-                                                                        s->thr_table + 132, T(e->cfg.G), s->a_sorted);
+                                                                        s->thr_table, T(e->cfg.G), s->a_sorted);
     e->launches += 2;
-    e->launches++;
   }
   if (e->cfg.world_size > 1) NBX_TRY(comm_allgather(e, s->a_sorted));
   unsort_kernel<T><<<(e->n + 255) / 256, 256, 0, e->stream>>>(s->perm, s->hilbert_targets ? s->order : nullptr, s->a_sorted, e->n,
@@ -880,7 +938,7 @@ static int stats_impl(nbx_engine* e, unsigned long long* dev_stats) {
                                                                                   s->thr_table, T(e->cfg.G), s->a_sorted, dev_stats);
     else
       octree_force_kernel<T, D, true><<<(nt + 127) / 128, 128, 0, e->stream>>>(s->mono, s->meta, s->root, s->cnt, s->hilbert_targets ? s->order : nullptr, e->n, e->tb, e->te,
-                                                                              s->thr_table + 132, T(e->cfg.G), s->a_sorted, dev_stats);
+                                                                              s->thr_table, T(e->cfg.G), s->a_sorted, dev_stats);
     e->launches += 2;
   }
   NBX_CUDA(cudaGetLastError());

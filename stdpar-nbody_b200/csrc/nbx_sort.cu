@@ -1,195 +1,217 @@
 // nbx_sort.cu — stable LSD radix sort of (u64 key, u32 index) pairs, hand-written for sm_100a (no CUB/Thrust).
 //
-// Replaces the reference's std::sort(par_unseq, pair<key,idx>) (src/bvh.h:62-69). 8 bits per pass; each pass is
-//   digit_histogram  : per-tile digit counts            -> hist[digit][tile]
-//   row_scan         : exclusive scan of every digit row (+ digit totals)
-//   scatter          : warp-match ranking (stable) + global offsets; the tile is first staged in shared memory in sorted
-//                      order so that the write-out is coalesced per digit run
-// A tile is RS_THREADS x RS_ITEMS consecutive elements laid out warp-striped, so loads are fully coalesced and the
-// element order inside a tile is (warp, iteration, lane) — ranks are assigned in exactly that order => STABLE, so ties
-// keep their current index order (the reference's unstable std::sort leaves ties undefined).
-// HBM traffic per pass: 8 B (histogram) + 12 B read + 12 B write per element.
+// Replaces the reference's std::sort(par_unseq, pair<key,idx>) (src/bvh.h:62-69). 8 bits per pass, ONE sweep over the
+// data per pass ("onesweep": Adinets & Merrill, "Onesweep: a faster least significant digit radix sort for GPUs", 2022):
+//   digit_histogram_kernel : one read of the keys (8 B/element) gives the digit totals of ALL passes at once; the same
+//                            kernel clears the tile-status words of the sweeps
+//   digit_scan_kernel      : exclusive scan of each pass's 256 totals -> first output position of every digit
+//   onesweep_kernel        : per pass; a CTA takes the next tile (atomic ticket => tiles start in index order), ranks its
+//                            elements per digit (warp-match ranking), publishes its per-digit counts, and obtains the
+//                            number of equal-digit elements in all EARLIER tiles by decoupled look-back over the status
+//                            words of its predecessors (a 32-bit word = 2 flag bits + 30-bit count, so no fence is
+//                            needed); the tile is staged in shared memory in sorted order and written out coalesced per
+//                            digit run.
+// A tile is OS_THREADS x ITEMS consecutive elements laid out warp-striped, so loads are fully coalesced and the element
+// order inside a tile is (warp, iteration, lane) = index order; ranks are assigned in exactly that order and tiles are
+// prefix-summed in index order => STABLE: ties keep their current index order (the reference's unstable std::sort leaves
+// ties undefined).
+// HBM traffic: 8 B/element once + per pass 12 B read + 12 B written (the last pass skips the keys when nobody wants them):
+// 8 + 24 * passes bytes per element, 10 launches for 64-bit keys (3 kernels x 8 passes = 24 launches and 32 B per
+// element and pass before).
 #include "nbx_internal.cuh"
 
 namespace nbx {
 
 namespace {
 
-constexpr int RS_THREADS = 512;
-constexpr int RS_ITEMS   = 8;
-constexpr int RS_TILE    = RS_THREADS * RS_ITEMS;  // 4096 elements
-constexpr int RS_WARPS   = RS_THREADS / 32;
-constexpr int RS_RADIX   = 256;
+#ifndef NBX_OS_THREADS
+#define NBX_OS_THREADS 512
+#endif
+#ifndef NBX_OS_ITEMS
+#define NBX_OS_ITEMS 8
+#endif
+constexpr int OS_THREADS = NBX_OS_THREADS;
+constexpr int OS_WARPS   = OS_THREADS / 32;
+constexpr int OS_RADIX   = 256;
+constexpr int OS_ITEMS   = NBX_OS_ITEMS;
+constexpr int OS_TILE    = OS_THREADS * OS_ITEMS;  // 4096 elements
+constexpr int OS_MAXPASS = 8;
+
+constexpr uint32_t ST_LOCAL = 1u << 30, ST_INCL = 2u << 30, ST_FLAGS = 3u << 30, ST_COUNT = ~ST_FLAGS;
 
 struct Sorter {
   uint32_t capacity = 0;
   uint32_t ntiles   = 0;
   uint64_t* keys[2] = {nullptr, nullptr};
   uint32_t* vals[2] = {nullptr, nullptr};
-  uint32_t* hist    = nullptr;  // [RS_RADIX][ntiles]
-  uint32_t* totals  = nullptr;  // [RS_RADIX]
+  uint32_t* ghist   = nullptr;  // [OS_MAXPASS][OS_RADIX] digit totals -> exclusive offsets; followed by [OS_MAXPASS] tickets
+  uint32_t* status  = nullptr;  // [OS_MAXPASS][ntiles][OS_RADIX]
 };
 
-__global__ void __launch_bounds__(RS_THREADS) digit_histogram_kernel(const uint64_t* __restrict__ keys, uint32_t n,
-                                                                     int shift, uint32_t* __restrict__ hist,
-                                                                     uint32_t ntiles) {
-  __shared__ uint32_t h[RS_RADIX];
-  for (int d = threadIdx.x; d < RS_RADIX; d += RS_THREADS) h[d] = 0;
+// digit totals of every pass in one read of the keys; also clears the status words of the sweeps that follow
+__global__ void __launch_bounds__(OS_THREADS) digit_histogram_kernel(const uint64_t* __restrict__ keys, uint32_t n, int passes,
+                                                                     uint32_t* __restrict__ ghist, uint32_t* __restrict__ status,
+                                                                     size_t status_words) {
+  __shared__ uint32_t h[OS_MAXPASS][OS_RADIX];
+  for (int q = threadIdx.x; q < OS_MAXPASS * OS_RADIX; q += OS_THREADS) (&h[0][0])[q] = 0;
+  for (size_t q = size_t(blockIdx.x) * OS_THREADS + threadIdx.x; q < status_words / 4; q += size_t(gridDim.x) * OS_THREADS)
+    reinterpret_cast<uint4*>(status)[q] = make_uint4(0, 0, 0, 0);
   __syncthreads();
-  const uint32_t base = blockIdx.x * RS_TILE;
+  for (uint32_t i = blockIdx.x * OS_THREADS + threadIdx.x; i < n; i += gridDim.x * OS_THREADS) {
+    const uint64_t k = keys[i];
 #pragma unroll
-  for (int k = 0; k < RS_ITEMS; ++k) {
-    uint32_t idx = base + (threadIdx.x >> 5) * (32 * RS_ITEMS) + k * 32 + (threadIdx.x & 31);
-    if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & 0xff], 1u);
+    for (int p = 0; p < OS_MAXPASS; ++p)
+      if (p < passes) atomicAdd(&h[p][(k >> (8 * p)) & 0xff], 1u);
   }
   __syncthreads();
-  for (int d = threadIdx.x; d < RS_RADIX; d += RS_THREADS) hist[size_t(d) * ntiles + blockIdx.x] = h[d];
+  for (int q = threadIdx.x; q < passes * OS_RADIX; q += OS_THREADS) {
+    const uint32_t c = (&h[0][0])[q];
+    if (c) atomicAdd(&ghist[q], c);
+  }
 }
 
-// one CTA per digit: exclusive scan of hist[d][0..ntiles) in place, total -> totals[d]
-__global__ void __launch_bounds__(1024) row_scan_kernel(uint32_t* hist, uint32_t ntiles, uint32_t* totals) {
-  __shared__ uint32_t warp_sums[32];
-  __shared__ uint32_t carry;
-  uint32_t* row = hist + size_t(blockIdx.x) * ntiles;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
+// one CTA per pass: exclusive scan of its 256 digit totals, in place
+__global__ void __launch_bounds__(OS_RADIX) digit_scan_kernel(uint32_t* ghist) {
+  __shared__ uint32_t ws[OS_RADIX / 32];
+  uint32_t* row = ghist + blockIdx.x * OS_RADIX;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (uint32_t base = 0; base < ntiles; base += 1024) {
-    uint32_t i = base + threadIdx.x;
-    uint32_t v = i < ntiles ? row[i] : 0;
-    uint32_t s = v;
+  const uint32_t v = row[threadIdx.x];
+  uint32_t s = v;
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      uint32_t t = __shfl_up_sync(0xffffffffu, s, off);
-      if (lane >= off) s += t;
-    }
-    if (lane == 31) warp_sums[warp] = s;
-    __syncthreads();
-    if (warp == 0) {
-      uint32_t w = warp_sums[lane];
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, w, off);
-        if (lane >= off) w += t;
-      }
-      warp_sums[lane] = w;  // inclusive
-    }
-    __syncthreads();
-    uint32_t prefix = carry + (warp ? warp_sums[warp - 1] : 0) + (s - v);
-    if (i < ntiles) row[i] = prefix;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = prefix + v;
-    __syncthreads();
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, s, off);
+    if (lane >= off) s += t;
   }
-  if (threadIdx.x == 0) totals[blockIdx.x] = carry;
+  if (lane == 31) ws[warp] = s;
+  __syncthreads();
+  uint32_t before = 0;
+  for (int w = 0; w < warp; ++w) before += ws[w];
+  row[threadIdx.x] = before + s - v;
 }
 
-// dynamic shared memory of scatter_kernel: per-warp digit counters + the tile staged in sorted order
-constexpr size_t RS_SMEM = sizeof(uint32_t) * RS_WARPS * RS_RADIX + sizeof(uint64_t) * RS_TILE + sizeof(uint32_t) * RS_TILE;
+// dynamic shared memory of onesweep_kernel: per-warp digit counters + the tile staged in sorted order
+constexpr size_t OS_SMEM = sizeof(uint32_t) * OS_WARPS * OS_RADIX + sizeof(uint64_t) * OS_TILE + sizeof(uint32_t) * OS_TILE;
 
-__global__ void __launch_bounds__(RS_THREADS) scatter_kernel(const uint64_t* __restrict__ keys_in,
-                                                             const uint32_t* __restrict__ vals_in,  // NULL => iota
-                                                             uint64_t* __restrict__ keys_out,
-                                                             uint32_t* __restrict__ vals_out, uint32_t n, int shift,
-                                                             const uint32_t* __restrict__ hist, uint32_t ntiles,
-                                                             const uint32_t* __restrict__ totals) {
-  extern __shared__ __align__(16) unsigned char rs_smem[];
-  uint32_t(*warp_count)[RS_RADIX] = reinterpret_cast<uint32_t(*)[RS_RADIX]>(rs_smem);
-  uint64_t* skey                  = reinterpret_cast<uint64_t*>(rs_smem + sizeof(uint32_t) * RS_WARPS * RS_RADIX);
-  uint32_t* sval                  = reinterpret_cast<uint32_t*>(skey + RS_TILE);
-  __shared__ uint32_t gbase[RS_RADIX];   // global position of this tile's first element of digit d
-  __shared__ uint32_t dstart[RS_RADIX];  // position of digit d inside the sorted tile
-  __shared__ uint32_t scan_tmp[RS_RADIX / 32];
-  __shared__ uint32_t scan_tmp2[RS_RADIX / 32];
+__global__ void __launch_bounds__(OS_THREADS) onesweep_kernel(const uint64_t* __restrict__ keys_in,
+                                                              const uint32_t* __restrict__ vals_in,  // NULL => iota
+                                                              uint64_t* __restrict__ keys_out,       // NULL => not wanted
+                                                              uint32_t* __restrict__ vals_out, uint32_t n, int shift,
+                                                              const uint32_t* __restrict__ digit_offset, uint32_t* status,
+                                                              uint32_t* ticket) {
+  extern __shared__ __align__(16) unsigned char os_smem[];
+  uint32_t(*warp_count)[OS_RADIX] = reinterpret_cast<uint32_t(*)[OS_RADIX]>(os_smem);
+  uint64_t* skey                  = reinterpret_cast<uint64_t*>(os_smem + sizeof(uint32_t) * OS_WARPS * OS_RADIX);
+  uint32_t* sval                  = reinterpret_cast<uint32_t*>(skey + OS_TILE);
+  __shared__ uint32_t goff[OS_RADIX];    // global position of this tile's first element of digit d, minus dstart[d]
+  __shared__ uint32_t dstart[OS_RADIX];  // position of digit d inside the sorted tile
+  __shared__ uint32_t scan_tmp[OS_RADIX / 32];
+  __shared__ uint32_t s_tile;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int q = threadIdx.x; q < RS_WARPS * RS_RADIX; q += RS_THREADS) (&warp_count[0][0])[q] = 0;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);  // tiles are handed out in launch order: every predecessor runs
+  for (int q = threadIdx.x; q < OS_WARPS * OS_RADIX; q += OS_THREADS) (&warp_count[0][0])[q] = 0;
+  __syncthreads();
+  const uint32_t tile  = s_tile;
+  const uint32_t tile0 = tile * OS_TILE;
 
-  // exclusive scan of the 256 digit totals (every CTA recomputes it: 256 values)
-  uint32_t tot = 0, inc = 0;
-  if (threadIdx.x < RS_RADIX) {
-    tot = totals[threadIdx.x];
-    inc = tot;
+  uint64_t key[OS_ITEMS];
+  uint32_t val[OS_ITEMS], rank[OS_ITEMS];
+  const uint32_t base = tile0 + warp * (32 * OS_ITEMS) + lane;
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
-      if (lane >= off) inc += t;
-    }
-    if (lane == 31) scan_tmp[warp] = inc;
+  for (int k = 0; k < OS_ITEMS; ++k) {
+    const uint32_t idx = base + k * 32;
+    key[k]             = idx < n ? keys_in[idx] : ~0ull;
+    val[k]             = idx < n ? (vals_in ? vals_in[idx] : idx) : 0xffffffffu;
+  }
+  // warp-match ranking: all lanes of a warp holding digit d in item k form `peers`; the lowest of them bumps the warp's
+  // counter of d by the group size (one shared-memory atomic, distinct addresses within the instruction) and hands the
+  // old value to its peers with a shuffle. The 8 matches are independent and issue back to back; the atomics of one
+  // warp execute in program order, so ranks follow (item, lane) order.
+  uint32_t peers[OS_ITEMS];
+#pragma unroll
+  for (int k = 0; k < OS_ITEMS; ++k) peers[k] = __match_any_sync(0xffffffffu, uint32_t(key[k] >> shift) & 0xff);
+#pragma unroll
+  for (int k = 0; k < OS_ITEMS; ++k) {
+    const uint32_t d      = uint32_t(key[k] >> shift) & 0xff;
+    const uint32_t lt     = peers[k] & ((1u << lane) - 1);
+    const int leader      = __ffs(peers[k]) - 1;
+    uint32_t old          = 0;
+    if (lt == 0) old = atomicAdd(&warp_count[warp][d], uint32_t(__popc(peers[k])));
+    rank[k] = __shfl_sync(0xffffffffu, old, leader) + __popc(lt);
   }
   __syncthreads();
-  if (threadIdx.x < RS_RADIX) {
-    uint32_t before = 0;
-    for (int w = 0; w < warp; ++w) before += scan_tmp[w];
-    gbase[threadIdx.x] = before + inc - tot + hist[size_t(threadIdx.x) * ntiles + blockIdx.x];
-  }
-
-  uint64_t key[RS_ITEMS];
-  uint32_t val[RS_ITEMS], rank[RS_ITEMS];
-  const uint32_t tile0 = blockIdx.x * RS_TILE;
-  const uint32_t base  = tile0 + warp * (32 * RS_ITEMS) + lane;
-#pragma unroll
-  for (int k = 0; k < RS_ITEMS; ++k) {
-    uint32_t idx = base + k * 32;
-    key[k]       = idx < n ? keys_in[idx] : ~0ull;
-    val[k]       = idx < n ? (vals_in ? vals_in[idx] : idx) : 0xffffffffu;
-  }
-  __syncthreads();  // warp_count zeroed, gbase ready
-#pragma unroll
-  for (int k = 0; k < RS_ITEMS; ++k) {
-    uint32_t d     = uint32_t(key[k] >> shift) & 0xff;
-    uint32_t peers = __match_any_sync(0xffffffffu, d);
-    uint32_t lt    = peers & ((1u << lane) - 1);
-    uint32_t cnt   = warp_count[warp][d];  // every peer reads the same value before the leader bumps it
-    __syncwarp();
-    if (lt == 0) warp_count[warp][d] = cnt + __popc(peers);
-    __syncwarp();
-    rank[k] = cnt + __popc(lt);
-  }
-  __syncthreads();
-  // per digit: exclusive prefix over the warps of this CTA, then over the digits (position inside the sorted tile)
+  // per digit (thread d): exclusive prefix over the warps of this CTA, publish the tile's count, position of the digit
+  // inside the sorted tile
   uint32_t dcount = 0, dinc = 0;
-  if (threadIdx.x < RS_RADIX) {
+  uint32_t* my_status = status + (size_t(tile) * OS_RADIX + threadIdx.x);
+  if (threadIdx.x < OS_RADIX) {
     uint32_t run = 0;
 #pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) {
-      uint32_t c                 = warp_count[w][threadIdx.x];
+    for (int w = 0; w < OS_WARPS; ++w) {
+      const uint32_t c           = warp_count[w][threadIdx.x];
       warp_count[w][threadIdx.x] = run;
       run += c;
     }
     dcount = run;
-    dinc   = run;
+    *reinterpret_cast<volatile uint32_t*>(my_status) = (tile == 0 ? ST_INCL : ST_LOCAL) | dcount;
+    dinc = run;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
-      uint32_t t = __shfl_up_sync(0xffffffffu, dinc, off);
+      const uint32_t t = __shfl_up_sync(0xffffffffu, dinc, off);
       if (lane >= off) dinc += t;
     }
-    if (lane == 31) scan_tmp2[warp] = dinc;
+    if (lane == 31) scan_tmp[warp] = dinc;
   }
   __syncthreads();
-  if (threadIdx.x < RS_RADIX) {
+  uint32_t my_dstart = 0;
+  if (threadIdx.x < OS_RADIX) {
     uint32_t before = 0;
-    for (int w = 0; w < warp; ++w) before += scan_tmp2[w];
-    dstart[threadIdx.x] = before + dinc - dcount;
+    for (int w = 0; w < warp; ++w) before += scan_tmp[w];
+    my_dstart           = before + dinc - dcount;
+    dstart[threadIdx.x] = my_dstart;
   }
   __syncthreads();
+  // decoupled look-back (digit threads): elements of digit d in all earlier tiles. It overlaps the staging done by the
+  // other warps; a predecessor that has not published yet is simply polled again.
+  if (threadIdx.x < OS_RADIX) {
+    // LB predecessors are read at once (independent loads in flight), then consumed nearest first; one that has not
+    // published yet is polled again. Rows before tile 0 count as "inclusive 0".
+    constexpr int LB = 8;
+    uint32_t excl = 0;
+    bool done     = tile == 0;
+    for (int64_t t = int64_t(tile) - 1; !done; t -= LB) {
+      uint32_t v[LB];
+#pragma unroll
+      for (int q = 0; q < LB; ++q)
+        v[q] = t - q >= 0 ? *reinterpret_cast<const volatile uint32_t*>(status + (size_t(t - q) * OS_RADIX + threadIdx.x)) : ST_INCL;
+#pragma unroll
+      for (int q = 0; q < LB; ++q) {
+        if (!done) {
+          while ((v[q] & ST_FLAGS) == 0) v[q] = *reinterpret_cast<const volatile uint32_t*>(status + (size_t(t - q) * OS_RADIX + threadIdx.x));
+          excl += v[q] & ST_COUNT;
+          done = (v[q] & ST_INCL) != 0;
+        }
+      }
+    }
+    if (tile != 0) *reinterpret_cast<volatile uint32_t*>(my_status) = ST_INCL | (excl + dcount);
+    goff[threadIdx.x] = digit_offset[threadIdx.x] + excl - my_dstart;
+  }
   // stage the tile in sorted order (stable: (warp, iteration, lane) order inside every digit)
 #pragma unroll
-  for (int k = 0; k < RS_ITEMS; ++k) {
-    uint32_t d  = uint32_t(key[k] >> shift) & 0xff;
-    uint32_t lp = dstart[d] + warp_count[warp][d] + rank[k];
-    skey[lp]    = key[k];
-    sval[lp]    = val[k];
+  for (int k = 0; k < OS_ITEMS; ++k) {
+    const uint32_t d  = uint32_t(key[k] >> shift) & 0xff;
+    const uint32_t lp = dstart[d] + warp_count[warp][d] + rank[k];
+    skey[lp]          = key[k];
+    sval[lp]          = val[k];
   }
   __syncthreads();
   // coalesced write-out: consecutive threads -> consecutive addresses inside every digit run. Elements past n carry the
-  // all-ones key, sort to the very end of the tile and are simply not written.
-  const uint32_t count = n - tile0 < uint32_t(RS_TILE) ? n - tile0 : uint32_t(RS_TILE);
-  for (uint32_t i = threadIdx.x; i < count; i += RS_THREADS) {
+  // all-ones key, sort to the very end of the (last) tile and are simply not written.
+  const uint32_t count = n - tile0 < uint32_t(OS_TILE) ? n - tile0 : uint32_t(OS_TILE);
+  for (uint32_t i = threadIdx.x; i < count; i += OS_THREADS) {
     const uint64_t kk = skey[i];
-    const uint32_t d  = uint32_t(kk >> shift) & 0xff;
-    const uint32_t gp = gbase[d] + (i - dstart[d]);
-    keys_out[gp]      = kk;
-    vals_out[gp]      = sval[i];
+    const uint32_t gp = goff[uint32_t(kk >> shift) & 0xff] + i;
+    if (keys_out) keys_out[gp] = kk;
+    vals_out[gp] = sval[i];
   }
 }
 
@@ -197,17 +219,18 @@ __global__ void __launch_bounds__(RS_THREADS) scatter_kernel(const uint64_t* __r
 
 int sorter_create(nbx_engine* e, uint32_t n) {
   if (e->sorter) return NBX_OK;
+  if (n >= (1u << 30)) return fail(NBX_ERR_INVALID, "sort: n must be below 2^30 (30-bit tile status counts)");
   Sorter* s   = new Sorter();
   e->sorter   = s;
   s->capacity = n;
-  s->ntiles   = (n + RS_TILE - 1) / RS_TILE;
+  s->ntiles   = (n + OS_TILE - 1) / OS_TILE;
   for (int k = 0; k < 2; ++k) {
     NBX_CUDA(cudaMalloc(&s->keys[k], sizeof(uint64_t) * size_t(n)));
     NBX_CUDA(cudaMalloc(&s->vals[k], sizeof(uint32_t) * size_t(n)));
   }
-  NBX_CUDA(cudaMalloc(&s->hist, sizeof(uint32_t) * size_t(RS_RADIX) * s->ntiles));
-  NBX_CUDA(cudaMalloc(&s->totals, sizeof(uint32_t) * RS_RADIX));
-  NBX_TRY(ensure_dynamic_smem(e, scatter_kernel, RS_SMEM));
+  NBX_CUDA(cudaMalloc(&s->ghist, sizeof(uint32_t) * (OS_MAXPASS * OS_RADIX + OS_MAXPASS)));
+  NBX_CUDA(cudaMalloc(&s->status, sizeof(uint32_t) * size_t(OS_MAXPASS) * s->ntiles * OS_RADIX));
+  NBX_TRY(ensure_dynamic_smem(e, onesweep_kernel, OS_SMEM));
   return NBX_OK;
 }
 
@@ -218,8 +241,8 @@ void sorter_destroy(nbx_engine* e) {
     if (s->keys[k]) cudaFree(s->keys[k]);
     if (s->vals[k]) cudaFree(s->vals[k]);
   }
-  if (s->hist) cudaFree(s->hist);
-  if (s->totals) cudaFree(s->totals);
+  if (s->ghist) cudaFree(s->ghist);
+  if (s->status) cudaFree(s->status);
   delete s;
   e->sorter = nullptr;
 }
@@ -229,20 +252,26 @@ int sort_pairs(nbx_engine* e, const uint64_t* keys_in, uint32_t n, int key_bits,
   NBX_TRY(sorter_create(e, n));
   Sorter* s = static_cast<Sorter*>(e->sorter);
   if (n > s->capacity) return fail(NBX_ERR_INVALID, "sort_pairs: n exceeds sorter capacity");
-  const uint32_t ntiles = (n + RS_TILE - 1) / RS_TILE;
+  const uint32_t ntiles = (n + OS_TILE - 1) / OS_TILE;
   int passes            = (key_bits + 7) / 8;
   if (passes < 1) passes = 1;
-  if (passes > 8) passes = 8;
+  if (passes > OS_MAXPASS) passes = OS_MAXPASS;
+  uint32_t* tickets = s->ghist + OS_MAXPASS * OS_RADIX;
+  NBX_CUDA(cudaMemsetAsync(s->ghist, 0, sizeof(uint32_t) * (OS_MAXPASS * OS_RADIX + OS_MAXPASS), e->stream));
+  const size_t status_words = size_t(passes) * ntiles * OS_RADIX;
+  const unsigned hgrid      = std::min<unsigned>(ntiles, unsigned(e->sm_count) * 4);
+  digit_histogram_kernel<<<hgrid, OS_THREADS, 0, e->stream>>>(keys_in, n, passes, s->ghist, s->status, status_words);
+  digit_scan_kernel<<<passes, OS_RADIX, 0, e->stream>>>(s->ghist);
+  e->launches += 2;
   const uint64_t* kin = keys_in;
   const uint32_t* vin = vals_in;  // nullptr => iota
   for (int p = 0; p < passes; ++p) {
     const bool last = p == passes - 1;
-    uint64_t* kout  = last && keys_sorted_out ? keys_sorted_out : s->keys[p & 1];
+    uint64_t* kout  = last ? keys_sorted_out : s->keys[p & 1];  // the last pass writes the keys only if somebody wants them
     uint32_t* vout  = last ? perm_out : s->vals[p & 1];
-    digit_histogram_kernel<<<ntiles, RS_THREADS, 0, e->stream>>>(kin, n, 8 * p, s->hist, ntiles);
-    row_scan_kernel<<<RS_RADIX, 1024, 0, e->stream>>>(s->hist, ntiles, s->totals);
-    scatter_kernel<<<ntiles, RS_THREADS, RS_SMEM, e->stream>>>(kin, vin, kout, vout, n, 8 * p, s->hist, ntiles, s->totals);
-    e->launches += 3;
+    onesweep_kernel<<<ntiles, OS_THREADS, OS_SMEM, e->stream>>>(kin, vin, kout, vout, n, 8 * p, s->ghist + p * OS_RADIX,
+                                                               s->status + size_t(p) * ntiles * OS_RADIX, tickets + p);
+    e->launches++;
     kin = kout;
     vin = vout;
   }

@@ -27,13 +27,13 @@ PHASES = ("force", "accel", "bbox", "sort", "build", "multipoles", "traverse", "
 
 # every symbol include/nbx.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
-    "nbx_last_error", "nbx_version", "nbx_device_count", "nbx_create", "nbx_destroy", "nbx_upload", "nbx_download",
+    "nbx_last_error", "nbx_version", "nbx_device_count", "nbx_create", "nbx_destroy", "nbx_upload", "nbx_download", "nbx_upload_shard", "nbx_download_shard",
     "nbx_step", "nbx_step_timed", "nbx_sync", "nbx_all_pairs_force", "nbx_all_pairs_collapsed_force",
     "nbx_accelerate_step", "nbx_calc_energies", "nbx_bvh_bounding_box", "nbx_bvh_hilbert_sort", "nbx_bvh_build_tree",
     "nbx_bvh_compute_force", "nbx_bvh_get_keys", "nbx_bvh_get_nodes", "nbx_octree_build", "nbx_octree_compute_force",
     "nbx_octree_get_root", "nbx_octree_get_canonical", "nbx_stream_positions_begin", "nbx_stream_positions_end",
     "nbx_comm_unique_id", "nbx_comm_init_rank",
-    "nbx_measure_fma_peak", "nbx_traversal_stats", "nbx_get_counters", "nbx_set_phase_timing", "nbx_get_phase_ms",
+    "nbx_measure_fma_peak", "nbx_traversal_stats", "nbx_walk_width", "nbx_get_counters", "nbx_set_phase_timing", "nbx_get_phase_ms",
 ]
 
 
@@ -130,6 +130,15 @@ class Engine:
     def upload(self, m=None, x=None, v=None, a=None, ao=None):
         m, x, v, a, ao = self._arr(m, 0), self._arr(x, 1), self._arr(v, 1), self._arr(a, 1), self._arr(ao, 1)
         _check(lib().nbx_upload(self._h, _p(m), _p(x), _p(v), _p(a), _p(ao)))
+
+    def upload_shard(self, m=None, x=None, v=None, a=None, ao=None):
+        """Collective: every rank copies only its shard of the (full) host arrays; the shards are all-gathered on the device."""
+        m, x, v, a, ao = self._arr(m, 0), self._arr(x, 1), self._arr(v, 1), self._arr(a, 1), self._arr(ao, 1)
+        _check(lib().nbx_upload_shard(self._h, _p(m), _p(x), _p(v), _p(a), _p(ao)))
+
+    def download_shard_into(self, m=None, x=None, v=None, a=None, ao=None):
+        """Writes this rank's shard of the bodies into the given full-size host arrays (other entries are left alone)."""
+        _check(lib().nbx_download_shard(self._h, _p(m), _p(x), _p(v), _p(a), _p(ao)))
 
     def upload_state(self, s):
         self.upload(s["m"], s["x"], s["v"], s["a"], s["ao"])
@@ -241,7 +250,9 @@ class Engine:
     def traversal_stats(self):
         v, a, w = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
         _check(lib().nbx_traversal_stats(self._h, C.byref(v), C.byref(a), C.byref(w)))
-        return dict(node_visits=v.value, interactions=a.value, warp_steps=w.value)
+        width = C.c_uint32(0)
+        _check(lib().nbx_walk_width(self._h, C.byref(width)))
+        return dict(node_visits=v.value, interactions=a.value, warp_steps=w.value, width=width.value)
 
     def set_phase_timing(self, enable=True):
         _check(lib().nbx_set_phase_timing(self._h, C.c_int(1 if enable else 0)))

@@ -159,7 +159,7 @@ def test_traversal_stats_match_oracle_visits(oracle_fast):
         e.bounding_box(); e.hilbert_sort(); e.build_tree()
         st = e.traversal_stats()
     assert st["node_visits"] == visits
-    assert st["warp_steps"] * 32 >= st["node_visits"] and st["interactions"] <= st["node_visits"]
+    assert st["warp_steps"] * st["width"] >= st["node_visits"] and st["interactions"] <= st["node_visits"]
 
 
 def test_bvh_full_pipeline_4M(oracle):

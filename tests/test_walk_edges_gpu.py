@@ -1,8 +1,8 @@
 """Edge cases of the warp-cooperative tree walks through the C ABI: tiny and power-of-two-boundary body counts, theta from 0
 (every leaf visited = all-pairs) to values that accept the root, against the oracle's walk of the same tree.
   bvh    : the (body, node) test count is EXACT (the test uses the reference's arithmetic), a within tolerance;
-  octree : the test count is exact in double (a flipped decision needs d2 within an ulp or two of the per-depth threshold),
-           within 1e-4 relative in float; a within tolerance."""
+  octree : the test count is EXACT in float and double (per-depth thresholds on dist2 found by bisection with the
+           reference's IEEE sqrt/div; the float walk evaluates the reference-order dist2); a within tolerance."""
 import numpy as np
 import pytest
 
@@ -67,10 +67,7 @@ def test_octree_walk_edges(oracle, dt, dim):
             # the reference also steps over EMPTY children (they contribute +0, octree.h:236-244); the record array has
             # no empty nodes, so the device count is compared with the oracle's count of non-empty tests
             want = oracle.octree_visits_nonempty(s["x"], t, theta)
-            if dt == np.float64:
-                assert st["node_visits"] == want, (n, theta, st, want)
-            else:
-                assert abs(st["node_visits"] - want) <= max(2, 1e-4 * want), (n, theta, st, want)
+            assert st["node_visits"] == want, (n, theta, st, want)  # float too: the decision is the reference's, exactly
             assert want <= visits
             check(a, ref, dt, ("octree", n, theta))
 
@@ -89,3 +86,20 @@ def test_octree_f64_interaction_count_is_theta_monotone(oracle_fast, theta):
     assert counts[0]["node_visits"] >= counts[1]["node_visits"]
     if theta == 0.0:
         assert counts[0]["interactions"] == n * n  # every leaf (incl. the body's own, which adds exactly 0) is accepted
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("theta", [0.3, 0.5, 0.9])
+def test_octree_interaction_set_is_the_references_at_50k(oracle, dt, theta):
+    """Identical accept/open decisions at a realistic size: the device's (body, node) test count equals the pinned
+    oracle's count of non-empty tests exactly — in float as well (per-depth thresholds found by bisection with IEEE
+    sqrt/div, compared with the reference-order dist2: csrc/nbx_octree.cu threshold_table_kernel)."""
+    n, dim = 50000, 3
+    s = oracle.galaxy(n, dt, dim)
+    t = oracle.octree_build(s["m"], s["x"])
+    want = oracle.octree_visits_nonempty(s["x"], t, theta)
+    with nbx.Engine(n, dim, dt, "octree", s["dt"], s["G"], theta=theta) as e:
+        e.upload_state(s)
+        e.octree_build(); e.octree_compute_force()
+        st = e.traversal_stats()
+    assert st["node_visits"] == want, (st, want)
