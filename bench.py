@@ -252,7 +252,14 @@ def make_state(n, dtype, dim):
     if not os.access(exe, os.X_OK):
         raise SystemExit(f"bench.py: {exe} is missing — build with __graft_entry__.build()")
     dtype = np.dtype(dtype)
-    shm = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    need = (2 * dim + 1) * dtype.itemsize * n * 10  # room for every rank of an 8-GPU run generating at once
+    shm = None
+    try:
+        st = os.statvfs("/dev/shm")
+        if os.access("/dev/shm", os.W_OK) and st.f_bavail * st.f_frsize > need:
+            shm = "/dev/shm"
+    except OSError:
+        pass
     with tempfile.TemporaryDirectory(dir=shm) as td:
         subprocess.run([exe, "-n", str(n), "-s", "1", "--workload", "galaxy", "--precision",
                         "float" if dtype == np.float32 else "double", "--dry-run", "--save", "pos"], cwd=td, check=True,

@@ -93,6 +93,7 @@ struct BvhState {
   vec4_t<T>* lo     = nullptr;
   vec4_t<T>* hi     = nullptr;
   bool have_box = false, sorted = false, built = false;
+  int sort_mode = 0;  // multi-GPU: 0 sharded, 1 replicated, 2 broadcast (NBX_BVH_SORT, read when the engine is created)
 };
 
 // ---- K10 bounding box ------------------------------------------------------------------------------------------
@@ -600,6 +601,11 @@ static int create_impl(nbx_engine* e) {
   while (nleafs < e->n) { nleafs <<= 1; ++levels; }
   if (levels > 30) return fail(NBX_ERR_INVALID, "bvh: n too large");
   s->levels  = levels;
+  {
+    const char* v = getenv("NBX_BVH_SORT");
+    const std::string m = v ? v : "sharded";
+    s->sort_mode = m == "broadcast" ? 2 : (m == "replicated" ? 1 : 0);
+  }
   s->nnodes  = (uint64_t(1) << levels) - 1;
   s->nblocks = std::min<uint32_t>((e->n + 255) / 256, uint32_t(e->sm_count) * 8);
   NBX_CUDA(cudaMalloc(&s->box, sizeof(Box<T>)));
@@ -655,16 +661,19 @@ static int sort_impl(nbx_engine* e) {
   auto* s = st<T>(e);
   if (!s->have_box) return fail(NBX_ERR_STATE, "hilbert_sort before bounding_box");
   const uint32_t n = e->n;
-  // Multi-GPU: every rank sorts the same keys (replicas; deterministic => identical permutations). The alternative of
-  // SURVEY §8(e3) — rank 0 sorts, the permutation is broadcast over NVLink — is kept behind NBX_BVH_SORT=broadcast for the
-  // measurement recorded in DESIGN.md §7: it cannot win, the other ranks only wait for rank 0 and then for 4 B/body more.
-  static const bool bcast = [] { const char* v = getenv("NBX_BVH_SORT"); return v && std::string(v) == "broadcast"; }();
-  if (!(bcast && e->cfg.world_size > 1 && e->cfg.rank != 0)) {
+  // Multi-GPU (measured in DESIGN.md §7): NBX_BVH_SORT = sharded (default: the ranks split the key range,
+  // sort_pairs_sharded) | replicated (every rank sorts all n keys; deterministic => identical permutations) | broadcast
+  // (rank 0 sorts, the permutation is broadcast over NVLink: the other ranks only wait). All three give the same bits.
+  const int mode = s->sort_mode;
+  const bool multi = e->cfg.world_size > 1;
+  const int bits   = D == 2 ? 64 : 63;
+  if (!(multi && mode == 2 && e->cfg.rank != 0)) {
     hilbert_keys_kernel<T, D><<<(n + 255) / 256, 256, 0, e->stream>>>(static_cast<const vec4_t<T>*>(e->xm[e->cur]), n, s->box, s->keys);
     e->launches++;
-    NBX_TRY(sort_pairs(e, s->keys, n, D == 2 ? 64 : 63, s->perm, nullptr));
+    if (multi && mode == 0) NBX_TRY(sort_pairs_sharded(e, s->keys, n, bits, s->perm));
+    else NBX_TRY(sort_pairs(e, s->keys, n, bits, s->perm, nullptr));
   }
-  if (bcast && e->cfg.world_size > 1) NBX_TRY(comm_broadcast(e, s->perm, sizeof(uint32_t) * size_t(n), 0));
+  if (multi && mode == 2) NBX_TRY(comm_broadcast(e, s->perm, sizeof(uint32_t) * size_t(n), 0));
   gather_kernel<T><<<(n + 255) / 256, 256, 0, e->stream>>>(
       s->perm, n, static_cast<const vec4_t<T>*>(e->xm[e->cur]), static_cast<vec4_t<T>*>(e->xm[e->cur ^ 1]),
       static_cast<const vec4_t<T>*>(e->v), static_cast<vec4_t<T>*>(e->v_alt), static_cast<const vec4_t<T>*>(e->a),

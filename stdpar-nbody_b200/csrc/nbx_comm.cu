@@ -29,6 +29,8 @@ struct NcclApi {
   ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t)                  = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t)             = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t)             = nullptr;
+  ncclResult_t (*GroupStart)()                                                                          = nullptr;
+  ncclResult_t (*GroupEnd)()                                                                            = nullptr;
   const char* (*GetErrorString)(ncclResult_t)                                                           = nullptr;
   bool ok = false;
 };
@@ -46,8 +48,10 @@ static void load_api(NcclApi& a) {
   a.AllGather      = (decltype(a.AllGather))dlsym(a.lib, "ncclAllGather");
   a.AllReduce      = (decltype(a.AllReduce))dlsym(a.lib, "ncclAllReduce");
   a.Broadcast      = (decltype(a.Broadcast))dlsym(a.lib, "ncclBroadcast");
+  a.GroupStart     = (decltype(a.GroupStart))dlsym(a.lib, "ncclGroupStart");
+  a.GroupEnd       = (decltype(a.GroupEnd))dlsym(a.lib, "ncclGroupEnd");
   a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.lib, "ncclGetErrorString");
-  a.ok             = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.AllReduce && a.Broadcast && a.GetErrorString;
+  a.ok             = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.AllReduce && a.Broadcast && a.GroupStart && a.GroupEnd && a.GetErrorString;
 }
 
 // the C++ driver calls in from one host thread per GPU: the table is filled exactly once, before anyone reads it
@@ -114,6 +118,20 @@ int comm_broadcast(nbx_engine* e, void* buffer, size_t bytes, int root) {
   if (!e->comm) return fail(NBX_ERR_COMM, "multi-GPU engine used before nbx_comm_init_rank");
   ncclResult_t r = api().Broadcast(buffer, buffer, bytes, ncclChar, root, (ncclComm_t)e->comm, e->stream);
   if (r != 0) return nccl_fail("ncclBroadcast", r);
+  return NBX_OK;
+}
+
+// all-gather with per-rank sizes: one grouped broadcast per owner
+int comm_allgatherv(nbx_engine* e, void* buffer, const size_t* offset, const size_t* count) {
+  if (e->cfg.world_size <= 1) return NBX_OK;
+  if (!e->comm) return fail(NBX_ERR_COMM, "multi-GPU engine used before nbx_comm_init_rank");
+  PhaseTimer pt(e, PH_COMM);
+  char* base     = static_cast<char*>(buffer);
+  ncclResult_t r = api().GroupStart();
+  for (int q = 0; q < e->cfg.world_size && r == 0; ++q)
+    if (count[q]) r = api().Broadcast(base + offset[q], base + offset[q], count[q], ncclChar, q, (ncclComm_t)e->comm, e->stream);
+  const ncclResult_t r2 = api().GroupEnd();
+  if (r != 0 || r2 != 0) return nccl_fail("grouped ncclBroadcast", r != 0 ? r : r2);
   return NBX_OK;
 }
 

@@ -172,6 +172,9 @@ void sorter_destroy(nbx_engine* e);
 // so that a second, more significant key can be sorted on top of an earlier permutation (LSD over two words).
 int sort_pairs(nbx_engine* e, const uint64_t* keys_in, uint32_t n, int key_bits, uint32_t* perm_out,
                uint64_t* keys_sorted_out, const uint32_t* vals_in = nullptr);
+// multi-GPU: the ranks split the key range between them (sample splitters, one partition sweep, per-rank sort, exchange
+// of the permutation segments); perm_out is bit-identical to sort_pairs'. Falls back to sort_pairs on one GPU / small n.
+int sort_pairs_sharded(nbx_engine* e, const uint64_t* keys_in, uint32_t n, int key_bits, uint32_t* perm_out);
 // nbx_bvh.cu
 int bvh_create(nbx_engine* e);
 void bvh_destroy(nbx_engine* e);
@@ -201,6 +204,8 @@ int comm_init_rank(nbx_engine* e, const void* id128);
 int comm_allgather(nbx_engine* e, void* vec4_array);  // in place: rank r contributes records [r*chunk, (r+1)*chunk)
 int comm_allreduce_sum(nbx_engine* e, void* buffer, size_t count);  // in place, `count` elements of the engine's precision
 int comm_broadcast(nbx_engine* e, void* buffer, size_t bytes, int root);
+// in place: rank q owns bytes [offset[q], offset[q] + count[q]) of `buffer`; afterwards every rank holds all of them
+int comm_allgatherv(nbx_engine* e, void* buffer, const size_t* offset, const size_t* count);
 void comm_destroy(nbx_engine* e);
 
 }  // namespace nbx

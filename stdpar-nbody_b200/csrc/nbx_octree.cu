@@ -421,13 +421,8 @@ __global__ void __launch_bounds__(256) group_cells_kernel(const uint32_t* __rest
   if (p != 0xffffffffu) cells_by_depth[base[d] + local] = p;
 }
 template <typename T, int D>
-__global__ void __launch_bounds__(256) monopole_level_kernel(const uint32_t* __restrict__ cells_by_depth, const uint32_t* __restrict__ depth_off,
-                                                             uint32_t depth, uint32_t cap, vec4_t<T>* mono, const uint2* __restrict__ meta) {
-  const uint32_t first = depth_off[depth], count = depth_off[depth + 1] - first;
-  uint32_t c = blockIdx.x * 256 + threadIdx.x;
-  if (c >= count) return;
-  const uint32_t p = cells_by_depth[first + c];
-  const uint2 me   = meta[p];
+__device__ __forceinline__ void monopole_cell(uint32_t p, uint32_t cap, vec4_t<T>* mono, const uint2* __restrict__ meta) {
+  const uint2 me = meta[p];
   T m = 0, x = 0, y = 0, z = 0;
   uint32_t q = p + 1;
   while (q < me.x && q < cap) {  // children in child order
@@ -439,6 +434,24 @@ __global__ void __launch_bounds__(256) monopole_level_kernel(const uint32_t* __r
     q = meta[q].x;
   }
   mono[p] = make_v4<T>(div_rn(x, m), div_rn(y, m), D == 3 ? div_rn(z, m) : T(0), m);
+}
+template <typename T, int D>
+__global__ void __launch_bounds__(256) monopole_level_kernel(const uint32_t* __restrict__ cells_by_depth, const uint32_t* __restrict__ depth_off,
+                                                             uint32_t depth, uint32_t cap, vec4_t<T>* mono, const uint2* __restrict__ meta) {
+  const uint32_t first = depth_off[depth], count = depth_off[depth + 1] - first;
+  uint32_t c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= count) return;
+  monopole_cell<T, D>(cells_by_depth[first + c], cap, mono, meta);
+}
+// depths `top` .. 0 in ONE launch when each holds at most 1024 cells (the top of every tree): a single CTA walks up
+template <typename T, int D>
+__global__ void __launch_bounds__(1024) monopole_top_kernel(const uint32_t* __restrict__ cells_by_depth, const uint32_t* __restrict__ depth_off,
+                                                            int top, uint32_t cap, vec4_t<T>* mono, const uint2* __restrict__ meta) {
+  for (int depth = top; depth >= 0; --depth) {
+    const uint32_t first = depth_off[depth], count = depth_off[depth + 1] - first;
+    if (threadIdx.x < count) monopole_cell<T, D>(cells_by_depth[first + threadIdx.x], cap, mono, meta);
+    __syncthreads();
+  }
 }
 
 // ---- target order of the walk ------------------------------------------------------------------------------------------
@@ -807,10 +820,12 @@ static int build_impl(nbx_engine* e) {
   // valid tree (monopoles, walk) is enqueued before the verdict, and an unusable tree is reported from here, before any
   // force kernel can walk it.
   NBX_TRY((build_attempt<T, D>(e, false)));
+  uint32_t hcount[130];  // cells per depth of the build (emit_records), read together with the verdict
   auto verdict = [&](uint32_t* ovf) -> int {
     NBX_CUDA(cudaMemcpyAsync(ovf, &s->root->overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    NBX_CUDA(cudaMemcpyAsync(hcount, s->depth_count, sizeof(hcount), cudaMemcpyDeviceToHost, e->stream));
     NBX_CUDA(cudaStreamSynchronize(e->stream));
-    e->d2h += sizeof(uint32_t);
+    e->d2h += sizeof(uint32_t) + sizeof(hcount);
     return NBX_OK;
   };
   uint32_t ovf = 0;
@@ -829,8 +844,20 @@ static int build_impl(nbx_engine* e) {
     const unsigned gc = (s->ccap + 255) / 256;
     group_cells_kernel<T><<<gc, 256, 0, e->stream>>>(s->cell_pos, s->root, s->meta, s->cap, s->depth_cursor, s->cells_by_depth);
     e->launches += 2;
-    for (int depth = (s->deep ? 2 : 1) * KeyTraits<D>::MAXL - 1; depth >= 0; --depth) {
-      monopole_level_kernel<T, D><<<gc, 256, 0, e->stream>>>(s->cells_by_depth, s->depth_count, uint32_t(depth), s->cap, s->mono, s->meta);
+    // one launch per populated depth, deepest first, sized by that depth's cell count; the sparse top of the tree (every
+    // depth from `top` up holding <= 1024 cells) goes into one single-CTA launch
+    int deepest = -1, top = -1;
+    for (int d = 0; d < 128; ++d)
+      if (hcount[d]) deepest = d;
+    for (int d = 0; d <= deepest && hcount[d] <= 1024u; ++d) top = d;
+    for (int depth = deepest; depth > top; --depth) {
+      if (!hcount[depth]) continue;
+      monopole_level_kernel<T, D><<<(hcount[depth] + 255) / 256, 256, 0, e->stream>>>(s->cells_by_depth, s->depth_count, uint32_t(depth), s->cap,
+                                                                                     s->mono, s->meta);
+      e->launches++;
+    }
+    if (top >= 0) {
+      monopole_top_kernel<T, D><<<1, 1024, 0, e->stream>>>(s->cells_by_depth, s->depth_count, top, s->cap, s->mono, s->meta);
       e->launches++;
     }
   }

@@ -39,6 +39,25 @@ constexpr int OS_MAXPASS = 8;
 
 constexpr uint32_t ST_LOCAL = 1u << 30, ST_INCL = 2u << 30, ST_FLAGS = 3u << 30, ST_COUNT = ~ST_FLAGS;
 
+// what a sweep partitions by: an 8-bit radix digit of the key, or — for the multi-GPU sharded sort — the rank that owns the
+// key's range: the number of splitters <= key (equal keys always share an owner, so the partition composes with the
+// per-rank sorts into the same stable order as one global sort)
+struct RadixDigit {
+  int shift;
+  __device__ __forceinline__ uint32_t operator()(uint64_t k) const { return uint32_t(k >> shift) & 0xff; }
+};
+constexpr int OS_MAXSPLIT = 15;
+struct OwnerDigit {
+  uint64_t split[OS_MAXSPLIT];  // ascending; unused entries = ~0ull are never <= a real key... unless the key is ~0ull:
+  int nsplit;                   // hence the explicit count
+  __device__ __forceinline__ uint32_t operator()(uint64_t k) const {
+    uint32_t d = 0;
+#pragma unroll
+    for (int q = 0; q < OS_MAXSPLIT; ++q) d += (q < nsplit) & (split[q] <= k);
+    return d;
+  }
+};
+
 struct Sorter {
   uint32_t capacity = 0;
   uint32_t ntiles   = 0;
@@ -46,7 +65,10 @@ struct Sorter {
   uint32_t* vals[2] = {nullptr, nullptr};
   uint32_t* ghist   = nullptr;  // [OS_MAXPASS][OS_RADIX] digit totals -> exclusive offsets; followed by [OS_MAXPASS] tickets
   uint32_t* status  = nullptr;  // [OS_MAXPASS][ntiles][OS_RADIX]
+  uint64_t* samples = nullptr;  // sharded sort: [2][OS_SAMPLES] sampled keys / sorted
+  uint32_t* sample_perm = nullptr;
 };
+constexpr uint32_t OS_SAMPLES = 1u << 16;
 
 // digit totals of every pass in one read of the keys; also clears the status words of the sweeps that follow
 __global__ void __launch_bounds__(OS_THREADS) digit_histogram_kernel(const uint64_t* __restrict__ keys, uint32_t n, int passes,
@@ -68,6 +90,40 @@ __global__ void __launch_bounds__(OS_THREADS) digit_histogram_kernel(const uint6
     const uint32_t c = (&h[0][0])[q];
     if (c) atomicAdd(&ghist[q], c);
   }
+}
+
+// sharded sort: elements per owner (one row of ghist), and the clearing of that sweep's status words
+__global__ void __launch_bounds__(OS_THREADS) owner_histogram_kernel(const uint64_t* __restrict__ keys, uint32_t n, const OwnerDigit digit,
+                                                                     uint32_t* __restrict__ ghist, uint32_t* __restrict__ status,
+                                                                     size_t status_words) {
+  __shared__ uint32_t h[OS_MAXSPLIT + 1];
+  if (threadIdx.x <= OS_MAXSPLIT) h[threadIdx.x] = 0;
+  for (size_t q = size_t(blockIdx.x) * OS_THREADS + threadIdx.x; q < status_words / 4; q += size_t(gridDim.x) * OS_THREADS)
+    reinterpret_cast<uint4*>(status)[q] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  uint32_t mine[OS_MAXSPLIT + 1];
+#pragma unroll
+  for (int q = 0; q <= OS_MAXSPLIT; ++q) mine[q] = 0;
+  for (uint32_t i = blockIdx.x * OS_THREADS + threadIdx.x; i < n; i += gridDim.x * OS_THREADS) {
+    const uint32_t d = digit(keys[i]);
+#pragma unroll
+    for (int q = 0; q <= OS_MAXSPLIT; ++q) mine[q] += d == uint32_t(q);
+  }
+#pragma unroll
+  for (int q = 0; q <= OS_MAXSPLIT; ++q) {
+    uint32_t v = mine[q];
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&h[q], v);
+  }
+  __syncthreads();
+  if (threadIdx.x <= OS_MAXSPLIT && h[threadIdx.x]) atomicAdd(&ghist[threadIdx.x], h[threadIdx.x]);
+}
+
+// evenly spaced sample of the keys (the same on every rank)
+__global__ void __launch_bounds__(256) sample_keys_kernel(const uint64_t* __restrict__ keys, uint32_t n, uint32_t nsamples,
+                                                          uint64_t* __restrict__ samples) {
+  const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+  if (i < nsamples) samples[i] = keys[uint64_t(i) * n / nsamples];
 }
 
 // one CTA per pass: exclusive scan of its 256 digit totals, in place
@@ -92,10 +148,11 @@ __global__ void __launch_bounds__(OS_RADIX) digit_scan_kernel(uint32_t* ghist) {
 // dynamic shared memory of onesweep_kernel: per-warp digit counters + the tile staged in sorted order
 constexpr size_t OS_SMEM = sizeof(uint32_t) * OS_WARPS * OS_RADIX + sizeof(uint64_t) * OS_TILE + sizeof(uint32_t) * OS_TILE;
 
+template <typename Digit>
 __global__ void __launch_bounds__(OS_THREADS) onesweep_kernel(const uint64_t* __restrict__ keys_in,
                                                               const uint32_t* __restrict__ vals_in,  // NULL => iota
                                                               uint64_t* __restrict__ keys_out,       // NULL => not wanted
-                                                              uint32_t* __restrict__ vals_out, uint32_t n, int shift,
+                                                              uint32_t* __restrict__ vals_out, uint32_t n, const Digit digit,
                                                               const uint32_t* __restrict__ digit_offset, uint32_t* status,
                                                               uint32_t* ticket) {
   extern __shared__ __align__(16) unsigned char os_smem[];
@@ -128,10 +185,10 @@ __global__ void __launch_bounds__(OS_THREADS) onesweep_kernel(const uint64_t* __
   // warp execute in program order, so ranks follow (item, lane) order.
   uint32_t peers[OS_ITEMS];
 #pragma unroll
-  for (int k = 0; k < OS_ITEMS; ++k) peers[k] = __match_any_sync(0xffffffffu, uint32_t(key[k] >> shift) & 0xff);
+  for (int k = 0; k < OS_ITEMS; ++k) peers[k] = __match_any_sync(0xffffffffu, digit(key[k]));
 #pragma unroll
   for (int k = 0; k < OS_ITEMS; ++k) {
-    const uint32_t d      = uint32_t(key[k] >> shift) & 0xff;
+    const uint32_t d      = digit(key[k]);
     const uint32_t lt     = peers[k] & ((1u << lane) - 1);
     const int leader      = __ffs(peers[k]) - 1;
     uint32_t old          = 0;
@@ -198,7 +255,7 @@ __global__ void __launch_bounds__(OS_THREADS) onesweep_kernel(const uint64_t* __
   // stage the tile in sorted order (stable: (warp, iteration, lane) order inside every digit)
 #pragma unroll
   for (int k = 0; k < OS_ITEMS; ++k) {
-    const uint32_t d  = uint32_t(key[k] >> shift) & 0xff;
+    const uint32_t d  = digit(key[k]);
     const uint32_t lp = dstart[d] + warp_count[warp][d] + rank[k];
     skey[lp]          = key[k];
     sval[lp]          = val[k];
@@ -209,7 +266,7 @@ __global__ void __launch_bounds__(OS_THREADS) onesweep_kernel(const uint64_t* __
   const uint32_t count = n - tile0 < uint32_t(OS_TILE) ? n - tile0 : uint32_t(OS_TILE);
   for (uint32_t i = threadIdx.x; i < count; i += OS_THREADS) {
     const uint64_t kk = skey[i];
-    const uint32_t gp = goff[uint32_t(kk >> shift) & 0xff] + i;
+    const uint32_t gp = goff[digit(kk)] + i;
     if (keys_out) keys_out[gp] = kk;
     vals_out[gp] = sval[i];
   }
@@ -230,7 +287,12 @@ int sorter_create(nbx_engine* e, uint32_t n) {
   }
   NBX_CUDA(cudaMalloc(&s->ghist, sizeof(uint32_t) * (OS_MAXPASS * OS_RADIX + OS_MAXPASS)));
   NBX_CUDA(cudaMalloc(&s->status, sizeof(uint32_t) * size_t(OS_MAXPASS) * s->ntiles * OS_RADIX));
-  NBX_TRY(ensure_dynamic_smem(e, onesweep_kernel, OS_SMEM));
+  if (e->cfg.world_size > 1) {
+    NBX_CUDA(cudaMalloc(&s->samples, sizeof(uint64_t) * 2 * OS_SAMPLES));
+    NBX_CUDA(cudaMalloc(&s->sample_perm, sizeof(uint32_t) * OS_SAMPLES));
+  }
+  NBX_TRY(ensure_dynamic_smem(e, onesweep_kernel<RadixDigit>, OS_SMEM));
+  NBX_TRY(ensure_dynamic_smem(e, onesweep_kernel<OwnerDigit>, OS_SMEM));
   return NBX_OK;
 }
 
@@ -243,6 +305,8 @@ void sorter_destroy(nbx_engine* e) {
   }
   if (s->ghist) cudaFree(s->ghist);
   if (s->status) cudaFree(s->status);
+  if (s->samples) cudaFree(s->samples);
+  if (s->sample_perm) cudaFree(s->sample_perm);
   delete s;
   e->sorter = nullptr;
 }
@@ -269,7 +333,7 @@ int sort_pairs(nbx_engine* e, const uint64_t* keys_in, uint32_t n, int key_bits,
     const bool last = p == passes - 1;
     uint64_t* kout  = last ? keys_sorted_out : s->keys[p & 1];  // the last pass writes the keys only if somebody wants them
     uint32_t* vout  = last ? perm_out : s->vals[p & 1];
-    onesweep_kernel<<<ntiles, OS_THREADS, OS_SMEM, e->stream>>>(kin, vin, kout, vout, n, 8 * p, s->ghist + p * OS_RADIX,
+    onesweep_kernel<RadixDigit><<<ntiles, OS_THREADS, OS_SMEM, e->stream>>>(kin, vin, kout, vout, n, RadixDigit{8 * p}, s->ghist + p * OS_RADIX,
                                                                s->status + size_t(p) * ntiles * OS_RADIX, tickets + p);
     e->launches++;
     kin = kout;
@@ -277,6 +341,60 @@ int sort_pairs(nbx_engine* e, const uint64_t* keys_in, uint32_t n, int key_bits,
   }
   NBX_CUDA(cudaGetLastError());
   return NBX_OK;
+}
+
+// Multi-GPU sharded sort (the alternative to every rank sorting all n keys). Every rank holds the same
+// keys. (1) 65536 evenly spaced keys are sorted and world-1 splitters read off at the quantiles — identical on every rank;
+// (2) ONE sweep partitions (key, index) by owner rank = number of splitters <= key, stably; (3) this rank radix-sorts
+// only its own key range (about n / world pairs); (4) the permutation segments are exchanged with one grouped NCCL
+// broadcast per owner. Equal keys share an owner and every stage is stable, so perm_out is bit-identical to sort_pairs'.
+// One small host synchronisation (the world segment sizes) per call.
+int sort_pairs_sharded(nbx_engine* e, const uint64_t* keys_in, uint32_t n, int key_bits, uint32_t* perm_out) {
+  NBX_TRY(sorter_create(e, n));
+  Sorter* s        = static_cast<Sorter*>(e->sorter);
+  const int world  = e->cfg.world_size, rank = e->cfg.rank;
+  if (world < 2 || world > OS_MAXSPLIT + 1 || !s->samples || n < 4 * OS_SAMPLES) return sort_pairs(e, keys_in, n, key_bits, perm_out, nullptr);
+  // (1) splitters
+  sample_keys_kernel<<<OS_SAMPLES / 256, 256, 0, e->stream>>>(keys_in, n, OS_SAMPLES, s->samples);
+  e->launches++;
+  NBX_TRY(sort_pairs(e, s->samples, OS_SAMPLES, key_bits, s->sample_perm, s->samples + OS_SAMPLES));
+  OwnerDigit od;
+  {
+    uint64_t h[OS_MAXSPLIT];
+    for (int q = 0; q < OS_MAXSPLIT; ++q) h[q] = ~0ull;
+    // the quantile keys are needed on the host to be passed by value: one tiny strided copy, one sync
+    NBX_CUDA(cudaMemcpy2DAsync(h, sizeof(uint64_t), s->samples + OS_SAMPLES + OS_SAMPLES / world, sizeof(uint64_t) * (OS_SAMPLES / world),
+                               sizeof(uint64_t), size_t(world - 1), cudaMemcpyDeviceToHost, e->stream));
+    NBX_CUDA(cudaStreamSynchronize(e->stream));
+    e->d2h += sizeof(uint64_t) * (world - 1);
+    for (int q = 0; q < OS_MAXSPLIT; ++q) od.split[q] = h[q];
+    od.nsplit = world - 1;
+  }
+  // (2) stable partition by owner into the sorter's second buffers
+  const uint32_t ntiles = (n + OS_TILE - 1) / OS_TILE;
+  uint32_t* tickets     = s->ghist + OS_MAXPASS * OS_RADIX;
+  NBX_CUDA(cudaMemsetAsync(s->ghist, 0, sizeof(uint32_t) * (OS_MAXPASS * OS_RADIX + OS_MAXPASS), e->stream));
+  const unsigned hgrid = std::min<unsigned>(ntiles, unsigned(e->sm_count) * 4);
+  owner_histogram_kernel<<<hgrid, OS_THREADS, 0, e->stream>>>(keys_in, n, od, s->ghist, s->status, size_t(ntiles) * OS_RADIX);
+  uint32_t counts[OS_MAXSPLIT + 1];
+  NBX_CUDA(cudaMemcpyAsync(counts, s->ghist, sizeof(uint32_t) * world, cudaMemcpyDeviceToHost, e->stream));
+  digit_scan_kernel<<<1, OS_RADIX, 0, e->stream>>>(s->ghist);
+  onesweep_kernel<OwnerDigit><<<ntiles, OS_THREADS, OS_SMEM, e->stream>>>(keys_in, nullptr, s->keys[1], s->vals[1], n, od, s->ghist, s->status, tickets);
+  e->launches += 3;
+  NBX_CUDA(cudaStreamSynchronize(e->stream));
+  e->d2h += sizeof(uint32_t) * world;
+  size_t offs[OS_MAXSPLIT + 2];
+  offs[0] = 0;
+  for (int q = 0; q < world; ++q) offs[q + 1] = offs[q] + counts[q];
+  if (offs[world] != n) return fail(NBX_ERR_STATE, "sharded sort: partition sizes do not add up");
+  // (3) my key range: sort_pairs ping-pongs through keys[0] / keys[1] from the front; its first pass has consumed the
+  // segment before anything is written over the partition buffer
+  const uint32_t cnt = counts[rank];
+  if (cnt) NBX_TRY(sort_pairs(e, s->keys[1] + offs[rank], cnt, key_bits, perm_out + offs[rank], nullptr, s->vals[1] + offs[rank]));
+  // (4) everybody gets every segment
+  size_t boff[OS_MAXSPLIT + 1], bcnt[OS_MAXSPLIT + 1];
+  for (int q = 0; q < world; ++q) { boff[q] = offs[q] * sizeof(uint32_t); bcnt[q] = size_t(counts[q]) * sizeof(uint32_t); }
+  return comm_allgatherv(e, perm_out, boff, bcnt);
 }
 
 }  // namespace nbx

@@ -40,6 +40,8 @@ def test_committed_sweep_log_through_the_references_scraper():
     assert all(x.split(",")[10] == "190" for x in nbx_rows)  # -s 200 minus the 10 hidden warm-up steps
     assert "B200" in nbx_rows[0].split(",")[0]
     check_rows(rows, len(rows) - 1)
+    ref_rows = [x for x in rows[1:] if ",gcc-omp-shim," in x]  # the unmodified reference's CPU build, bounded sizes
+    assert len(ref_rows) in (0, 6)
     # the tool's restatement of the scraper agrees with the real one, line for line
     assert ref_sweep.parse_log(open(LOG).read().splitlines()) == rows
 

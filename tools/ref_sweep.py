@@ -104,7 +104,9 @@ def main():
     ap.add_argument("--precision", default="double")             # ci/benchmark:14
     ap.add_argument("--dim", type=int, default=3, choices=[2, 3])
     ap.add_argument("--reference", action="store_true", help="also sweep the unmodified reference CPU build")
-    ap.add_argument("--reference-steps", type=int, default=12)
+    ap.add_argument("--reference-steps", type=int, default=11)     # 10 hidden warm-up steps + 1 timed
+    ap.add_argument("--reference-small", type=int, default=20_000, help="CPU arm: a bounded sample of the sizes")
+    ap.add_argument("--reference-large", type=int, default=200_000)
     ap.add_argument("--reference-only", action="store_true")
     ap.add_argument("--csv", action="store_true", help="print the scraped CSV (ci/data.py format) instead of the raw log")
     args = ap.parse_args()
@@ -122,7 +124,7 @@ def main():
     if args.reference or args.reference_only:
         exe = os.path.join(ROOT, "oracle", "_ref", f"nbody_d{args.dim}_omp")
         threads = len(os.sched_getaffinity(0))
-        run_matrix(exe, "gcc-omp-shim", out, args.reference_steps, args.small, args.large, args.precision, threads)
+        run_matrix(exe, "gcc-omp-shim", out, args.reference_steps, args.reference_small, args.reference_large, args.precision, threads)
     if args.csv:
         print("\n".join(parse_log(log)))
 
