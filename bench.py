@@ -349,7 +349,9 @@ def hbm_phase_bytes(cfg, n, isz):
         out["sort"] = (rec + 8) * n + (8 + passes * 24) * n + (4 + 8 * rec) * n
     elif cfg.algorithm == "octree":
         passes = 8
-        out["sort"] = (rec + 8) * n + (8 + passes * 24) * n
+        # path keys (read x, write key) + onesweep sort (keys kept: the cells are found on the sorted keys) + delta (read the
+        # sorted keys, write delta + cell counts); from n = 4 M also the Hilbert lane order: coarse keys + a 4-pass sort
+        out["sort"] = (rec + 8) * n + (8 + passes * 24) * n + 16 * n + ((16 + 8 + 4 * 24 - 8) * n if n >= (4 << 20) else 0)
     return out
 
 
