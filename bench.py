@@ -338,15 +338,19 @@ class Ctx:
         return eng
 
 
-def hbm_phase_bytes(cfg, n, isz):
-    """Algorithmic HBM bytes of the phases that stream the body arrays once: what the kernels must move."""
+def hbm_phase_bytes(cfg, n, isz, world=1):
+    """Algorithmic HBM bytes PER RANK of the phases that stream the body arrays once: what the kernels must
+    move."""
     rec = 4 * isz
     out = {"accel": 7 * rec * n}  # leapfrog: read x,v,a,ao + write x,v,ao (system.h:52-60)
     if cfg.algorithm == "bvh":
         passes = 8
         # keys (read x, write key) + onesweep radix sort (one 8 B histogram read, then 12 B in + 12 B out per pass) +
         # gather of x,v,a,ao through the permutation
-        out["sort"] = (rec + 8) * n + (8 + passes * 24) * n + (4 + 8 * rec) * n
+        sort = (8 + passes * 24) * n
+        if world > 1 and n >= (1 << 18):  # sharded: owner histogram + one partition sweep over n, radix passes over n / world
+            sort = 8 * n + 24 * n + (8 + passes * 24) * (n // world) + 4 * n
+        out["sort"] = (rec + 8) * n + sort + (4 + 8 * rec) * n
     elif cfg.algorithm == "octree":
         passes = 8
         # path keys (read x, write key) + onesweep sort (keys kept: the cells are found on the sorted keys) + delta (read the
@@ -406,7 +410,7 @@ def roofline_tree(ctx, cfg, n, dim, dt, ph, st, targets, clk):
         r["hbm_frac"] = r["dram_gbs"] / hbm_peak
     # the phases that really stream HBM: algorithmic bytes / phase time / measured HBM peak
     phases = []
-    for name, b in hbm_phase_bytes(cfg, n, isz).items():
+    for name, b in hbm_phase_bytes(cfg, n, isz, ctx.world).items():
         ms = ph.get(name)
         if ms:
             gbs = b / (ms * 1e-3) / 1e9

@@ -40,6 +40,48 @@ print("GLOO_OK", rank)
 '''
 
 
+# The data flow of the multi-GPU sharded sort (csrc/nbx_sort.cu sort_pairs_sharded), restated with torch + gloo: evenly spaced
+# sample -> sorted -> world-1 splitters at the quantiles; owner = number of splitters <= key; stable partition by owner;
+# every rank sorts (stably) only its own key range; segments exchanged with one broadcast per owner. The result must be the
+# global STABLE sort permutation whatever the key distribution (ties never straddle two owners).
+SHARDED_SORT_WORKER = r'''
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+rng = np.random.default_rng(7)  # same keys on every rank, like the replicated Hilbert keys
+for n, dist_name in ((300001, "uniform"), (262144, "ties"), (500000, "clustered")):
+    if dist_name == "uniform":
+        keys = rng.integers(0, 2**63, n, dtype=np.uint64)
+    elif dist_name == "ties":
+        keys = rng.integers(0, 50, n, dtype=np.uint64) << np.uint64(40)   # only 50 distinct keys: many owners may be empty
+    else:
+        keys = (rng.normal(2**40, 2**20, n).clip(0, 2**62)).astype(np.uint64)
+    S = 65536
+    sample = np.sort(keys[(np.arange(S, dtype=np.uint64) * np.uint64(n) // np.uint64(S)).astype(np.int64)], kind="stable")
+    split = sample[[q * (S // world) for q in range(1, world)]]
+    owner = (split[None, :] <= keys[:, None]).sum(1)
+    part = np.argsort(owner, kind="stable")                                # the partition sweep: stable, by owner
+    counts = np.bincount(owner, minlength=world)
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    mine = part[offs[rank]:offs[rank + 1]]
+    perm = np.full(n, -1, np.int64)
+    perm[offs[rank]:offs[rank + 1]] = mine[np.argsort(keys[mine], kind="stable")]   # this rank sorts its key range only
+    t = torch.from_numpy(perm)
+    for q in range(world):                                                  # grouped broadcast, one per owner
+        if counts[q]:
+            seg = t[offs[q]:offs[q + 1]].clone()
+            dist.broadcast(seg, src=q)
+            t[offs[q]:offs[q + 1]] = seg
+    want = np.argsort(keys, kind="stable")
+    assert np.array_equal(t.numpy(), want), (dist_name, rank)
+dist.barrier()
+dist.destroy_process_group()
+print("SHARDED_SORT_OK", rank)
+'''
+
+
 def torchrun(args, env=None, timeout=600):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29561"] + args
@@ -53,6 +95,14 @@ def test_gloo_world2_sharding(tmp_path):
     r = torchrun([str(script)])
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("GLOO_OK") == 2
+
+
+def test_gloo_world2_sharded_sort_equals_global_stable_sort(tmp_path):
+    script = tmp_path / "sharded_sort_worker.py"
+    script.write_text(SHARDED_SORT_WORKER)
+    r = torchrun([str(script)])
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("SHARDED_SORT_OK") == 2
 
 
 def test_reference_arm_under_torchrun_prints_once():
