@@ -2,15 +2,12 @@
 // copy + mbarrier PTX wrappers, L2-only vec4 accesses and the leapfrog update.
 #pragma once
 #include "nbx_internal.cuh"
+#include "nbx_math.cuh"
 
 namespace nbx {
 
-// round-to-nearest ops that the compiler may not contract: the leapfrog restates system.h:56-58 operation by
-// operation so that, given the same `a`, it is bit-identical to the pinned (-ffp-contract=off) reference.
-__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+// (mul_rn / add_rn: nbx_math.cuh. The leapfrog restates system.h:56-58 operation by operation so that, given the same
+// `a`, it is bit-identical to the pinned reference.)
 
 // ---- TMA bulk copy + mbarrier helpers (PTX) -------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

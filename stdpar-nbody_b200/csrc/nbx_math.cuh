@@ -8,6 +8,19 @@
 
 namespace nbx {
 
+// ---- exact arithmetic ---------------------------------------------------------------------------------------------------
+// Round-to-nearest operations that the compiler may not contract into FMAs: everything that feeds an integer artefact, a
+// tree node, an accept/open decision or the leapfrog restates the reference's expressions operation by operation with
+// these, so that the results are bit-identical to the pinned (-ffp-contract=off) reference.
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+
 // ---- 1 / (d2^1.5 + eps)   (vec.h:249-252 dist3; all-pairs and bvh) ---------------------------------------------------
 // d2 == 0 gives 1/eps (finite), so a self / coincident pair contributes m * 0 * (1/eps) = 0 exactly as the reference's
 // m*(pj-pi)/dist3 does, without a branch.
