@@ -145,6 +145,35 @@ __global__ void __launch_bounds__(OS_RADIX) digit_scan_kernel(uint32_t* ghist) {
   row[threadIdx.x] = before + s - v;
 }
 
+// lanes of the warp holding the same 8-bit digit. MATCH.ANY does this in one instruction, but on B200 it sustains only about
+// one warp instruction per 114 cycles per scheduler (measured with %globaltimer inside this kernel: 3.7 us of a 9.5 us tile for
+// 8 matches per thread); eight ballots — one per digit bit, each ANDed in plain or complemented — cost about 32 ALU
+// instructions per item and are faster.
+__device__ __forceinline__ uint32_t digit_peers(uint32_t d) {
+#ifdef NBX_OS_USE_MATCH
+  return __match_any_sync(0xffffffffu, d);
+#else
+  // four instructions per bit (test -> predicate, ballot, select the complement mask, combine); written in PTX because the
+  // compiler otherwise re-derives each bit from the 64-bit key shift and spends 5-6
+  uint32_t peers = 0xffffffffu;
+#pragma unroll
+  for (int b = 0; b < 8; ++b)
+    asm("{\n"
+        ".reg .pred p;\n"
+        ".reg .b32 t, bal, m;\n"
+        "and.b32 t, %1, %2;\n"
+        "setp.ne.u32 p, t, 0;\n"
+        "vote.sync.ballot.b32 bal, p, 0xffffffff;\n"
+        "selp.b32 m, 0, 0xffffffff, p;\n"
+        "xor.b32 bal, bal, m;\n"  // lanes whose bit b equals mine
+        "and.b32 %0, %0, bal;\n"
+        "}\n"
+        : "+r"(peers)
+        : "r"(d), "r"(1u << b));
+  return peers;
+#endif
+}
+
 // dynamic shared memory of onesweep_kernel: per-warp digit counters + the tile staged in sorted order
 constexpr size_t OS_SMEM = sizeof(uint32_t) * OS_WARPS * OS_RADIX + sizeof(uint64_t) * OS_TILE + sizeof(uint32_t) * OS_TILE;
 
@@ -185,7 +214,11 @@ __global__ void __launch_bounds__(OS_THREADS) onesweep_kernel(const uint64_t* __
   // warp execute in program order, so ranks follow (item, lane) order.
   uint32_t peers[OS_ITEMS];
 #pragma unroll
-  for (int k = 0; k < OS_ITEMS; ++k) peers[k] = __match_any_sync(0xffffffffu, digit(key[k]));
+#ifndef NBX_OS_NMATCH
+#define NBX_OS_NMATCH 0
+#endif
+  for (int k = 0; k < OS_ITEMS; ++k)  // the first NBX_OS_NMATCH items on the MATCH unit, the others on ballots
+    peers[k] = k < NBX_OS_NMATCH ? __match_any_sync(0xffffffffu, digit(key[k])) : digit_peers(digit(key[k]));
 #pragma unroll
   for (int k = 0; k < OS_ITEMS; ++k) {
     const uint32_t d      = digit(key[k]);
@@ -232,7 +265,10 @@ __global__ void __launch_bounds__(OS_THREADS) onesweep_kernel(const uint64_t* __
   if (threadIdx.x < OS_RADIX) {
     // LB predecessors are read at once (independent loads in flight), then consumed nearest first; one that has not
     // published yet is polled again. Rows before tile 0 count as "inclusive 0".
-    constexpr int LB = 8;
+#ifndef NBX_OS_LB
+#define NBX_OS_LB 4
+#endif
+    constexpr int LB = NBX_OS_LB;
     uint32_t excl = 0;
     bool done     = tile == 0;
     for (int64_t t = int64_t(tile) - 1; !done; t -= LB) {
@@ -243,7 +279,12 @@ __global__ void __launch_bounds__(OS_THREADS) onesweep_kernel(const uint64_t* __
 #pragma unroll
       for (int q = 0; q < LB; ++q) {
         if (!done) {
-          while ((v[q] & ST_FLAGS) == 0) v[q] = *reinterpret_cast<const volatile uint32_t*>(status + (size_t(t - q) * OS_RADIX + threadIdx.x));
+          while ((v[q] & ST_FLAGS) == 0) {
+#ifdef NBX_OS_SLEEP
+            __nanosleep(NBX_OS_SLEEP);
+#endif
+            v[q] = *reinterpret_cast<const volatile uint32_t*>(status + (size_t(t - q) * OS_RADIX + threadIdx.x));
+          }
           excl += v[q] & ST_COUNT;
           done = (v[q] & ST_INCL) != 0;
         }
