@@ -168,9 +168,16 @@ __device__ __forceinline__ void skilling2(uint32_t& x0, uint32_t& x1, int bits) 
     }
   }
   x1 ^= x0;  // Gray encode
-  uint32_t t = 0;
-  for (uint32_t Q = M; Q > 1; Q >>= 1)
-    if (x1 & Q) t ^= Q - 1;
+  // the reference's loop `for (Q = M; Q > 1; Q >>= 1) if (x1 & Q) t ^= Q - 1;` (vec.h:318-323) sets bit j of t to the
+  // parity of the bits of x1 above j, up to bit `bits`-1 (a cell index that rounded up to 2^bits carries a higher bit, which
+  // the loop never looks at): a suffix XOR in five doubling steps, shifted down by one
+  uint32_t t = x1 & ((M << 1) - 1u);
+  t ^= t >> 1;
+  t ^= t >> 2;
+  t ^= t >> 4;
+  t ^= t >> 8;
+  t ^= t >> 16;
+  t >>= 1;
   x0 ^= t;
   x1 ^= t;
 }

@@ -25,9 +25,14 @@ __device__ __forceinline__ uint64_t hilbert_index(uint32_t (&X)[D], int HB) {
   }
 #pragma unroll
   for (int k = 1; k < D; ++k) X[k] ^= X[k - 1];
-  uint32_t t = 0;
-  for (uint32_t Q = M; Q > 1; Q >>= 1)
-    if (X[D - 1] & Q) t ^= Q - 1;
+  // t_j = parity of the bits of X[D-1] above j (Skilling's loop `if (X[D-1] & Q) t ^= Q - 1` in closed form)
+  uint32_t t = X[D - 1] & ((M << 1) - 1u);
+  t ^= t >> 1;
+  t ^= t >> 2;
+  t ^= t >> 4;
+  t ^= t >> 8;
+  t ^= t >> 16;
+  t >>= 1;
   uint64_t h = 0;
   for (int j = HB - 1; j >= 0; --j)
 #pragma unroll
