@@ -30,6 +30,9 @@ namespace {
 #ifndef NBX_OS_ITEMS
 #define NBX_OS_ITEMS 8
 #endif
+#ifndef NBX_OS_MINB
+#define NBX_OS_MINB 1
+#endif
 constexpr int OS_THREADS = NBX_OS_THREADS;
 constexpr int OS_WARPS   = OS_THREADS / 32;
 constexpr int OS_RADIX   = 256;
@@ -178,7 +181,7 @@ __device__ __forceinline__ uint32_t digit_peers(uint32_t d) {
 constexpr size_t OS_SMEM = sizeof(uint32_t) * OS_WARPS * OS_RADIX + sizeof(uint64_t) * OS_TILE + sizeof(uint32_t) * OS_TILE;
 
 template <typename Digit>
-__global__ void __launch_bounds__(OS_THREADS) onesweep_kernel(const uint64_t* __restrict__ keys_in,
+__global__ void __launch_bounds__(OS_THREADS, NBX_OS_MINB) onesweep_kernel(const uint64_t* __restrict__ keys_in,
                                                               const uint32_t* __restrict__ vals_in,  // NULL => iota
                                                               uint64_t* __restrict__ keys_out,       // NULL => not wanted
                                                               uint32_t* __restrict__ vals_out, uint32_t n, const Digit digit,
