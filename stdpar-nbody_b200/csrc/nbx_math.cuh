@@ -60,6 +60,9 @@ __device__ __forceinline__ float sq_plus_tiny(float dx) { return dx * dx; }  // 
 __device__ __forceinline__ double sq_plus_tiny(double dx) { return fma(dx, dx, 1e-300); }
 __device__ __forceinline__ float inv_dist3_pos(float d2) { return inv_dist3(d2); }
 __device__ __forceinline__ double inv_dist3_pos(double d2) {  // requires d2 > 0
+  // (One seed instead of two — y = d2^-1/2, y^3 (1 - eps y^3), the two-seed form only for d2 < 1e-6 — saves 2 of the 25 DP
+  // operations per unordered pair on paper; measured at n = 262 144: 93.3 instead of 56.7 ms per step — the data-dependent
+  // branch breaks the register-blocked loop, as the float one-MUFU trial did. Not kept.)
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d2));
   const double t = d2 * y;
