@@ -505,7 +505,10 @@ int all_pairs_force(nbx_engine* e, bool fuse_integrate) {
   if (all_pairs_sym_enabled(e)) {
     rc = all_pairs_sym_force(e, fuse_integrate);
     if (rc == NBX_OK && fuse_integrate) e->cur ^= 1;
-    return rc;
+    // the symmetric kernel's partial-sum buffer does not fit: on one GPU fall back to the ordered sweep for good (same
+    // result up to summation order); on several GPUs every rank must take the same path, so the error stands
+    if (rc != NBX_ERR_CAPACITY || e->cfg.world_size > 1) return rc;
+    e->sym_unavailable = true;
   }
   const bool small = e->n < 32768;  // 128-body tiles give small problems 4x more CTAs to spread over the 148 SMs
   if (e->prec == 4) {
@@ -563,7 +566,9 @@ int all_pairs_collapsed_force(nbx_engine* e) {
     // large n: the block-pair units of the symmetric kernel ARE the pair-parallel decomposition, with the symmetry the
     // reference's TODO asks for (all_pairs.h:41-42); the collapsed semantics (2 components, a -= ao reset) live in the finish
     const int nc = (e->cfg.flags & NBX_FLAG_COLLAPSED_FIX_Z) && e->dim == 3 ? 3 : 2;
-    return all_pairs_sym_force(e, false, nc);
+    const int rcs = all_pairs_sym_force(e, false, nc);
+    if (rcs != NBX_ERR_CAPACITY || e->cfg.world_size > 1) return rcs;
+    e->sym_unavailable = true;  // buffer does not fit: the pair-parallel kernel below serves instead
   }
   int rc;
   if (e->prec == 4) rc = e->dim == 2 ? launch_collapsed<float, 2>(e) : launch_collapsed<float, 3>(e);

@@ -458,9 +458,15 @@ static int sym_launch(nbx_engine* e, bool fuse, int nc) {
     const size_t bytes   = sizeof(vec4_t<T>) * size_t(2) * s->B * size_t(mine ? mine : 1);
     size_t free_b = 0, total_b = 0;
     NBX_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    if (bytes + (size_t(512) << 20) > free_b)
+    // NBX_SYM_MAX_MB caps the buffer (tests of the fallback below)
+    const char* cap_env = getenv("NBX_SYM_MAX_MB");  // read per allocation (once per engine)
+    const size_t cap_mb = cap_env ? size_t(atoll(cap_env)) : size_t(0);
+    if (bytes + (size_t(512) << 20) > free_b || (cap_mb && (bytes >> 20) >= cap_mb)) {
+      delete s;
+      e->sym = nullptr;
       return fail(NBX_ERR_CAPACITY, "symmetric all-pairs: the partial-sum buffer needs " + std::to_string(bytes >> 20) + " MiB, " +
                                         std::to_string(free_b >> 20) + " MiB are free; create the engine with NBX_FLAG_ALLPAIRS_ORDERED");
+    }
     NBX_CUDA(cudaMalloc(&s->P, bytes));
     NBX_CUDA(cudaMalloc(&s->asum, sizeof(vec4_t<T>) * e->n_pad));
   }
@@ -518,6 +524,7 @@ static int sym_launch(nbx_engine* e, bool fuse, int nc) {
 }
 
 bool all_pairs_sym_enabled(const nbx_engine* e) {
+  if (e->sym_unavailable) return false;
   if ((e->algo != NBX_ALL_PAIRS && e->algo != NBX_ALL_PAIRS_COLLAPSED) || (e->cfg.flags & NBX_FLAG_ALLPAIRS_ORDERED)) return false;
   if (e->cfg.flags & NBX_FLAG_ALLPAIRS_SYMMETRIC) return true;
   return e->n >= 16384;  // measured cross-over on B200; below that there are too few (I, J) units to fill 148 SMs

@@ -100,6 +100,7 @@ struct nbx_engine {
   void* octree = nullptr;
   void* sorter = nullptr;
   void* sym = nullptr;  // symmetric all-pairs state (nbx_allpairs_sym.cu)
+  bool sym_unavailable = false;  // its partial-sum buffer did not fit (single GPU): the ordered kernel serves instead
 
   // NCCL (multi-GPU)
   void* comm = nullptr;

@@ -284,3 +284,21 @@ def test_collapsed_symmetric_path(oracle_fast, tag, dim):
         assert rms(err) <= max(tol_rms, 1e-12) and err.max() <= max(tol_max, 2e-11), (rms(err), err.max())
     if dim == 3:
         assert same(out["a"][:, 2], s["a"][:, 2])
+
+
+def test_symmetric_buffer_too_large_falls_back_to_the_ordered_kernel(oracle_fast, monkeypatch):
+    """When the partial-sum buffer of the symmetric kernel does not fit, a single-GPU engine serves the step with the
+    ordered sweep instead (advisor finding: no bare cudaMalloc failure): bit-identical to an engine created with
+    NBX_FLAG_ALLPAIRS_ORDERED."""
+    monkeypatch.setenv("NBX_SYM_MAX_MB", "1")
+    n, dim = 30000, 3
+    for algo in ("all-pairs", "all-pairs-collapsed"):
+        s = oracle_fast.galaxy(n, np.float32, dim)
+        outs = []
+        for flags in (0, nbx.FLAG_ALLPAIRS_ORDERED):
+            with nbx.Engine(n, dim, np.float32, algo, s["dt"], s["G"], flags=flags) as e:
+                e.upload_state(s)
+                e.step(3)
+                outs.append(e.download())
+        for k in ("x", "v", "a", "ao"):
+            assert outs[0][k].tobytes() == outs[1][k].tobytes(), (algo, k)
