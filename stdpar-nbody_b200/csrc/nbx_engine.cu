@@ -195,8 +195,7 @@ static int bvh_step_enqueue(nbx_engine* e) {
 // host work and most of the gaps between the small kernels (what small n is bound by). NBX_GRAPH=0 disables it; phase
 // timing (events between the kernels) and multi-GPU steps (NCCL calls) use the plain launch sequence.
 static int bvh_step(nbx_engine* e) {
-  static const bool enabled = [] { const char* v = getenv("NBX_GRAPH"); return !(v && atoi(v) == 0); }();
-  if (!enabled || e->phase_timing || e->cfg.world_size > 1) return bvh_step_enqueue(e);
+  if (!e->use_graph || e->phase_timing || e->cfg.world_size > 1) return bvh_step_enqueue(e);
   const int par = e->cur;
   if (e->step_graph[par] && e->step_graph_v[par] == e->v) {
     NBX_CUDA(cudaGraphLaunch(e->step_graph[par], e->stream));
@@ -307,6 +306,10 @@ int nbx_create(const nbx_config* cfg, nbx_engine** out) {
   e->algo = cfg->algorithm;
   e->n    = cfg->n;
   e->device = cfg->device;
+  {
+    const char* v = getenv("NBX_GRAPH");
+    e->use_graph  = !(v && atoi(v) == 0);
+  }
   e->chunk  = (cfg->n + cfg->world_size - 1) / cfg->world_size;
   e->n_pad  = e->chunk * cfg->world_size;
   e->tb     = std::min<uint64_t>(uint64_t(e->chunk) * cfg->rank, cfg->n);

@@ -107,6 +107,7 @@ struct nbx_engine {
 
   // CUDA graph of one BVH time step (single GPU: the step has no host decision). The step flips the position buffer
   // and swaps v/a/ao with their alternates, so there is one graph per parity of `cur`.
+  bool use_graph = true;  // NBX_GRAPH=0 (read when the engine is created) disables the replay
   cudaGraphExec_t step_graph[2] = {nullptr, nullptr};
   uint64_t step_graph_launches[2] = {0, 0};
   const void* step_graph_v[2] = {nullptr, nullptr};  // e->v when the graph was captured (must match at replay)

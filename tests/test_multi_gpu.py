@@ -121,3 +121,23 @@ def test_reference_arm_under_torchrun_prints_once():
 def test_nccl_multi_gpu_matches_single_gpu():
     r = torchrun([os.path.join(ROOT, "tests", "multi_gpu_check.py")], timeout=900)
     assert r.returncode == 0 and "MULTI_GPU_CHECK PASS" in r.stdout, r.stdout[-4000:] + r.stderr[-4000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(nbx.device_count() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("algo,prec", [("all-pairs", "float"), ("bvh", "float"), ("octree", "double"), ("all-pairs-collapsed", "double")])
+def test_cpp_driver_gpus2_prints_the_single_gpu_state(algo, prec):
+    """The C++ host driver's `--gpus 2` (one engine + host thread per GPU inside one process): the printed final state —
+    positions, velocities AND accelerations of rank 0's replicated copy — equals the single-GPU run's (trees bit-exact;
+    all-pairs may differ in the last printed digit on a couple of lines)."""
+    exe = os.path.join(ROOT, "stdpar-nbody_b200", "bin", "nbody_d3")
+    n = "300000" if algo == "bvh" else "2000"  # bvh: large enough for the sharded sort
+    args = ["-n", n, "-s", "12", "--workload", "galaxy", "--algorithm", algo, "--precision", prec, "--theta", "0.5", "--print-state"]
+    one = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600)
+    two = subprocess.run([exe] + args + ["--gpus", "2"], capture_output=True, text=True, timeout=600)
+    assert one.returncode == 0 and two.returncode == 0, one.stderr + two.stderr
+    a = [ln for ln in one.stdout.splitlines() if not ln.startswith("Total time")]
+    b = [ln for ln in two.stdout.splitlines() if not ln.startswith("Total time")]
+    assert len(a) == len(b) and len(a) > int(n)
+    bad = [(x, y) for x, y in zip(a, b) if x != y]
+    assert len(bad) <= (0 if algo in ("bvh", "octree") else 2), bad[:3]

@@ -81,3 +81,20 @@ def test_ten_steps_n4096(oracle, algo, dt, dim):
                                      ("bvh", np.float64)], ids=["all-pairs-f32", "octree-f32", "octree-f64", "bvh-f32", "bvh-f64"])
 def test_ten_steps_n65536(oracle_fast, algo, dt):
     check(oracle_fast, algo, dt, 3, 65536)
+
+
+def test_c1_all_pairs_2d_float_n10k_5_steps(oracle):
+    """BASELINE.json configs[0], the reference's own CPU-runnable case: all-pairs galaxy D = 2 float, n = 10 000, 5 steps —
+    positions AND velocities against the pinned oracle (the engine takes its one-launch ordered kernel at this size)."""
+    n, dim, steps = 10_000, 2, 5
+    s = oracle.galaxy(n, np.float32, dim)
+    with nbx.Engine(n, dim, np.float32, "all-pairs", s["dt"], s["G"]) as e:
+        e.upload_state(s)
+        e.step(steps)
+        out = e.download()
+    ref = oracle.run("all-pairs", s, steps)
+    ex, ev = rel_err(out["x"], ref["x"]), rel_err(out["v"], ref["v"])
+    assert rms(ex) <= 1e-6 and float(np.median(ex)) <= 1e-7, (rms(ex), float(np.median(ex)))
+    assert rms(ev) <= 1e-4, rms(ev)
+    ea = rel_err(out["a"], ref["a"])
+    assert rms(ea) <= 5e-5, rms(ea)
