@@ -519,7 +519,7 @@ def measure(ctx, cfg, steps, warmup, want_e2e, want_cpu, s=None):
     if cfg.algorithm.startswith("all-pairs"):
         roofline = roofline_all_pairs(ctx, cfg, n, dim, dt, ph, world)
         try:  # DRAM traffic of the dominant kernel from the committed ncu capture of this exact workload (1 GPU), if any
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(workload_name(cfg, n))
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(workload_name(cfg, n))
             if tr and world == 1:
                 roofline["traffic"] = tr["bytes"]
                 roofline["traffic_source"] = "profiles/" + tr["source"]
