@@ -80,8 +80,8 @@ struct BvhState {
   uint32_t* perm   = nullptr;
   vec4_t<T>* node_m = nullptr;  // (com.x, com.y, com.z, mass)
   T* bw             = nullptr;
-  T* bw2            = nullptr;  // bw*bw (rounded once, as bvh.h:247 does per test)
-  WalkRec<T>* rec   = nullptr;  // what the traversal loads: (com, mass, bw^2) of node k in ONE aligned record
+  WalkRec<T>* rec   = nullptr;  // what the traversal loads: (com, mass, bw*bw) of node k in ONE aligned record; bw*bw is
+                                // rounded once at build time, as bvh.h:247 rounds it per test
   vec4_t<T>* lo     = nullptr;
   vec4_t<T>* hi     = nullptr;
   bool have_box = false, sorted = false, built = false;
