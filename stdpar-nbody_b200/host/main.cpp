@@ -323,7 +323,12 @@ struct Engines {
       check(nbx_create(&c, &e[r]), "nbx_create");
     }
     if (o.gpus > 1) each([&](int r) { check(nbx_comm_init_rank(e[r], id), "nbx_comm_init_rank"); });
-    each([&](int r) { check(nbx_upload(e[r], s.m.data(), s.x.data(), s.v.data(), s.a.data(), s.ao.data()), "nbx_upload"); });
+    // every engine ends up with the full replicated state; with several GPUs each one copies only its shard of the bodies
+    // over PCIe and the shards are all-gathered over NVLink (a collective: all host threads call it)
+    each([&](int r) {
+      if (o.gpus > 1) check(nbx_upload_shard(e[r], s.m.data(), s.x.data(), s.v.data(), s.a.data(), s.ao.data()), "nbx_upload_shard");
+      else check(nbx_upload(e[r], s.m.data(), s.x.data(), s.v.data(), s.a.data(), s.ao.data()), "nbx_upload");
+    });
   }
   ~Engines() {
     for (auto* p : e) nbx_destroy(p);
