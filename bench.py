@@ -334,8 +334,29 @@ class Ctx:
             ids = [nbx.comm_unique_id() if rank == 0 else None]
             self.dist.broadcast_object_list(ids, src=0)
             eng.comm_init_rank(ids[0])
+            if cfg.algorithm == "bvh" and os.environ.get("NBX_PEER", "0") == "1":  # opt-in: see DESIGN.md §7
+                self.peer_setup(eng)
         eng.upload_state(s)
         return eng
+
+    def peer_setup(self, eng):
+        """Peer-memory exchange of the BVH accelerations (nbx_peer_export / nbx_peer_import): CUDA IPC handles gathered
+        through torch.distributed. All ranks agree on the outcome; where IPC is not available the NCCL all-gather stays."""
+        nbx, torch = self.nbx, self.torch
+        ok = 1
+        try:
+            handles = [None] * self.world
+            self.dist.all_gather_object(handles, eng.peer_export())
+            eng.peer_import(handles)
+        except nbx.NbxError as ex:
+            ok = 0
+            if self.rank == 0:
+                print(f"bench.py: peer buffers unavailable ({ex}); using the NCCL all-gather", file=sys.stderr, flush=True)
+        t = torch.tensor([ok], device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        self.peer = bool(int(t.item()))
+        if not self.peer:
+            eng.peer_import(None)
 
 
 def hbm_phase_bytes(cfg, n, isz, world=1):
@@ -512,7 +533,9 @@ def measure(ctx, cfg, steps, warmup, want_e2e, want_cpu, s=None):
     elif cfg.algorithm.startswith("all-pairs"):
         parallelism = f"targets sharded x{world}, NCCL all-gather of accelerations"
     else:
-        parallelism = f"replicated tree build, traversal sharded x{world}, NCCL all-gather of accelerations"
+        parallelism = (f"traversal sharded x{world}, accelerations stored into the peers' arrays by the walk kernel (P2P over "
+                       "NVLink) + barrier; sharded Hilbert sort, replicated tree build" if cfg.algorithm == "bvh" and getattr(ctx, "peer", False)
+                       else f"replicated tree build, traversal sharded x{world}, NCCL all-gather of accelerations")
     if rank != 0:
         return None, s
     clk = clocks.summary(t_region0, t_region1)
@@ -664,7 +687,11 @@ def verify_multi(ctx, cases=VERIFY_CASES, log=None):
     t = torch.tensor([1 if ok_all else 0], device="cuda")
     if ctx.dist:
         ctx.dist.all_reduce(t, op=ctx.dist.ReduceOp.MIN)
-    return {"ok": bool(int(t.item())), "ranks": ctx.world, "cases": results,
+    exchange = ("bvh: accelerations stored into the peers' arrays by the walk kernel (CUDA IPC, P2P over NVLink) + barrier"
+                if getattr(ctx, "peer", False) else "bvh: NCCL all-gather of the accelerations")
+    if log and ctx.rank == 0:
+        log(f"[rank 0/{ctx.world}] exchange paths checked: {exchange}; all-pairs: NCCL all-reduce / all-gather; octree: NCCL all-gather")
+    return {"ok": bool(int(t.item())), "ranks": ctx.world, "cases": results, "exchange": exchange,
             "what": "N-GPU engine vs single-GPU engine on the same inputs, every rank checks the full replicated state"}
 
 

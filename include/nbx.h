@@ -152,6 +152,19 @@ int nbx_stream_positions_end(nbx_engine* e, void* x_host);
 int nbx_comm_unique_id(void* id128);
 int nbx_comm_init_rank(nbx_engine* e, const void* id128);
 
+/* Peer-memory exchange for the BVH walk (one process per GPU on one NVLink/NVSwitch box). By default a rank's
+ * accelerations reach the other ranks with an ncclAllGather after the walk. With peer buffers the walk kernel itself
+ * stores every finished body's acceleration into ALL ranks' arrays (P2P stores over NVLink, overlapped with the walk
+ * warp by warp) and only a barrier follows. nbx_peer_export writes this engine's two CUDA IPC memory handles (the
+ * acceleration array alternates between two buffers, src/bvh.h:71-91 permutes every step); the caller gathers the
+ * NBX_PEER_HANDLE_BYTES of every rank (rank order) and passes them to nbx_peer_import, which fails with NBX_ERR_COMM —
+ * leaving the NCCL path in place — where CUDA IPC is not available; nbx_peer_import(e, NULL) drops the peer buffers again.
+ * EVERY rank must end up on the same path (the caller agrees on it, e.g. with an all-reduce of the return codes).
+ * Needs nbx_comm_init_rank first; NBX_BVH engines. */
+#define NBX_PEER_HANDLE_BYTES 128
+int nbx_peer_export(nbx_engine* e, void* handle128);
+int nbx_peer_import(nbx_engine* e, const void* handles_world_x_128);
+
 /* ---- measurement helpers ---------------------------------------------------------------------------------- */
 /* FMA-pipe peak microbenchmark on the engine's device: precision NBX_F32 -> FFMA, NBX_F64 -> DFMA.
  * *tflops = 2 * fma/s / 1e12 measured with CUDA events. */

@@ -427,10 +427,18 @@ __global__ void __launch_bounds__(128) bvh_force_kernel(const vec4_t<T>* __restr
 // 10257 / 11499 / 13339 steps per warp for NB = 1 / 2 / 4). In float the NB tests run two at a time on FP32x2
 // instructions (add/mul.rn.f32x2 round each half exactly like the scalar ops, and are never contracted), so decisions
 // stay bit-identical to the reference's.
+// the other ranks' acceleration arrays (CUDA IPC views, nbx_peer_import): the walk stores each finished body's result
+// into every one of them — P2P stores over NVLink issued warp by warp while the other warps still walk — instead of an
+// all-gather after the kernel. count = 0: single GPU, or the NCCL path.
+struct PeerOut {
+  void* p[15];
+  int count;
+};
+
 template <typename T, int D, int NB, bool COUNT = false>
 __global__ void __launch_bounds__(128) bvh_force_key_kernel(const vec4_t<T>* __restrict__ xm, const WalkRec<T>* __restrict__ rec1,
                                                             uint32_t n, uint32_t tb, uint32_t te, uint32_t levels, T theta2, T c,
-                                                            vec4_t<T>* __restrict__ a_out, unsigned long long* stats = nullptr) {
+                                                            vec4_t<T>* __restrict__ a_out, unsigned long long* stats, const PeerOut peers) {
   // rec1 is the record array offset by -1 element: indexed by the 1-based heap index kk = k + 1
   constexpr bool PACK = sizeof(T) == 4 && NB % 2 == 0;  // FP32x2 over pairs of bodies
   const uint32_t lane  = threadIdx.x & 31u;
@@ -561,7 +569,12 @@ __global__ void __launch_bounds__(128) bvh_force_key_kernel(const vec4_t<T>* __r
   } else {
 #pragma unroll
     for (int j = 0; j < NB; ++j)
-      if (idx[j] < te) a_out[idx[j]] = make_v4<T>(mul_rn(c, ax[j]), mul_rn(c, ay[j]), D == 3 ? mul_rn(c, az[j]) : T(0), T(0));
+      if (idx[j] < te) {
+        const vec4_t<T> r = make_v4<T>(mul_rn(c, ax[j]), mul_rn(c, ay[j]), D == 3 ? mul_rn(c, az[j]) : T(0), T(0));
+        a_out[idx[j]] = r;
+        for (int q = 0; q < peers.count; ++q) static_cast<vec4_t<T>*>(peers.p[q])[idx[j]] = r;
+      }
+    if (peers.count) __threadfence_system();
   }
 }
 
@@ -629,6 +642,8 @@ static int create_impl(nbx_engine* e) {
     NBX_CUDA(cudaMalloc(pp, rb * e->n_pad));
     NBX_CUDA(cudaMemsetAsync(*pp, 0, rb * e->n_pad, e->stream));
   }
+  e->own_a[0] = e->a;
+  e->own_a[1] = e->a_alt;
   NBX_TRY(sorter_create(e, e->n));
   return NBX_OK;
 }
@@ -736,7 +751,13 @@ static int launch_walk(nbx_engine* e, BvhState<T>* s, unsigned long long* stats)
   const auto* xm    = static_cast<const vec4_t<T>*>(e->xm[e->cur]);
   auto* a           = static_cast<vec4_t<T>*>(e->a);
   const unsigned grid = (nt + 128u * nb - 1) / (128u * nb);
-#define NBX_WALK(NB_) bvh_force_key_kernel<T, D, NB_, COUNT><<<grid, 128, 0, e->stream>>>(xm, s->rec - 1, e->n, e->tb, e->te, s->levels, theta * theta, T(e->cfg.G), a, stats)
+  PeerOut peers{};
+  if (!COUNT && e->peers_ready && e->cfg.world_size > 1) {
+    const int k = e->a == e->own_a[0] ? 0 : 1;  // which of its two buffers `a` is right now (the same on every rank)
+    for (int r = 0; r < e->cfg.world_size; ++r)
+      if (r != e->cfg.rank) peers.p[peers.count++] = e->peer_a[k][r];
+  }
+#define NBX_WALK(NB_) bvh_force_key_kernel<T, D, NB_, COUNT><<<grid, 128, 0, e->stream>>>(xm, s->rec - 1, e->n, e->tb, e->te, s->levels, theta * theta, T(e->cfg.G), a, stats, peers)
   if (nb == 1) NBX_WALK(1);
   else if (nb == 2) NBX_WALK(2);
   else NBX_WALK(4);
@@ -848,12 +869,18 @@ int bvh_build_tree(nbx_engine* e) {
   return BVH_DISPATCH(e, build_impl, e);
 }
 int bvh_compute_force(nbx_engine* e) {
+  // Peer stores land in the OTHER ranks' acceleration arrays, which their own gather (hilbert_sort) has just written:
+  // no rank may start storing before every rank is past its build. Without this barrier a fast rank's results were
+  // overwritten by a slower rank's gather — seen on 8 GPUs at n = 50 021 (1 ms steps), not at n = 10 M.
+  if (e->cfg.world_size > 1 && e->peers_ready) NBX_TRY(comm_barrier(e));
   {
     PhaseTimer pt(e, PH_TRAVERSE);
     NBX_TRY(BVH_DISPATCH(e, force_impl, e));
   }
-  // multi-GPU: a[tb, te) of every rank -> the full acceleration array everywhere (replicated state)
-  return e->cfg.world_size > 1 ? comm_allgather(e, e->a) : NBX_OK;
+  // multi-GPU: a[tb, te) of every rank -> the full acceleration array everywhere (replicated state): either the walk stored
+  // its results into the peers' arrays itself and only a barrier is left, or one NCCL all-gather
+  if (e->cfg.world_size <= 1) return NBX_OK;
+  return e->peers_ready ? comm_barrier(e) : comm_allgather(e, e->a);
 }
 int bvh_stats(nbx_engine* e, unsigned long long* dev_stats) { return BVH_DISPATCH(e, stats_impl, e, dev_stats); }
 // what sort_impl / build_impl do on the host besides enqueueing kernels; a replayed graph step needs the same

@@ -9,6 +9,8 @@
 // resolves to torch's bundled libnccl.so.2, in the C++ driver to the system one).
 #include <dlfcn.h>
 
+#include <cstring>
+
 #include <mutex>
 
 #include "nbx_internal.cuh"
@@ -19,7 +21,7 @@ namespace {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
-constexpr int ncclChar = 0, ncclFloat = 7, ncclDouble = 8, ncclSum = 0;
+constexpr int ncclChar = 0, ncclInt = 2, ncclFloat = 7, ncclDouble = 8, ncclSum = 0;
 
 struct NcclApi {
   void* lib = nullptr;
@@ -135,7 +137,79 @@ int comm_allgatherv(nbx_engine* e, void* buffer, const size_t* offset, const siz
   return NBX_OK;
 }
 
+// stream-ordered barrier over the ranks: a 4-byte all-reduce
+int comm_barrier(nbx_engine* e) {
+  if (e->cfg.world_size <= 1) return NBX_OK;
+  if (!e->comm) return fail(NBX_ERR_COMM, "multi-GPU engine used before nbx_comm_init_rank");
+  PhaseTimer pt(e, PH_COMM);
+  if (!e->barrier_scratch) {
+    NBX_CUDA(cudaMalloc(&e->barrier_scratch, sizeof(int)));
+    NBX_CUDA(cudaMemsetAsync(e->barrier_scratch, 0, sizeof(int), e->stream));
+  }
+  ncclResult_t r = api().AllReduce(e->barrier_scratch, e->barrier_scratch, 1, ncclInt, ncclSum, (ncclComm_t)e->comm, e->stream);
+  if (r != 0) return nccl_fail("ncclAllReduce (barrier)", r);
+  return NBX_OK;
+}
+
+// ---- peer buffers (CUDA IPC) --------------------------------------------------------------------------------------------
+int peer_export(nbx_engine* e, void* handle128) {
+  if (!handle128) return fail(NBX_ERR_INVALID, "handle buffer is NULL");
+  if (e->algo != NBX_BVH || !e->own_a[0] || !e->own_a[1]) return fail(NBX_ERR_STATE, "peer buffers exist for NBX_BVH engines only");
+  static_assert(2 * sizeof(cudaIpcMemHandle_t) == NBX_PEER_HANDLE_BYTES, "handle size");
+  cudaIpcMemHandle_t h[2];
+  for (int k = 0; k < 2; ++k) {
+    cudaError_t err = cudaIpcGetMemHandle(&h[k], e->own_a[k]);
+    if (err != cudaSuccess) {
+      cudaGetLastError();
+      return fail(NBX_ERR_COMM, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(err));
+    }
+  }
+  memcpy(handle128, h, sizeof(h));
+  return NBX_OK;
+}
+
+int peer_import(nbx_engine* e, const void* handles) {
+  if (!handles) {  // back to the NCCL all-gather (every rank must take the same path: the caller agrees on it)
+    peer_close(e);
+    return NBX_OK;
+  }
+  const int world = e->cfg.world_size, rank = e->cfg.rank;
+  if (world < 2 || world > 16) return fail(NBX_ERR_INVALID, "peer buffers need 2..16 ranks");
+  if (e->algo != NBX_BVH || !e->own_a[0]) return fail(NBX_ERR_STATE, "peer buffers exist for NBX_BVH engines only");
+  if (!e->comm) return fail(NBX_ERR_COMM, "nbx_peer_import before nbx_comm_init_rank");
+  peer_close(e);
+  const cudaIpcMemHandle_t* h = static_cast<const cudaIpcMemHandle_t*>(handles);
+  for (int r = 0; r < world; ++r)
+    for (int k = 0; k < 2; ++k) {
+      if (r == rank) { e->peer_a[k][r] = e->own_a[k]; continue; }
+      cudaIpcMemHandle_t hh;
+      memcpy(&hh, &h[2 * r + k], sizeof(hh));
+      void* p = nullptr;
+      cudaError_t err = cudaIpcOpenMemHandle(&p, hh, cudaIpcMemLazyEnablePeerAccess);
+      if (err != cudaSuccess) {
+        cudaGetLastError();
+        peer_close(e);
+        return fail(NBX_ERR_COMM, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(err) + " (the NCCL all-gather stays in use)");
+      }
+      e->peer_a[k][r] = p;
+    }
+  e->peers_ready = true;
+  return NBX_OK;
+}
+
+void peer_close(nbx_engine* e) {
+  for (int k = 0; k < 2; ++k)
+    for (int r = 0; r < 16; ++r) {
+      if (e->peer_a[k][r] && e->peer_a[k][r] != e->own_a[k]) cudaIpcCloseMemHandle(e->peer_a[k][r]);
+      e->peer_a[k][r] = nullptr;
+    }
+  e->peers_ready = false;
+}
+
 void comm_destroy(nbx_engine* e) {
+  peer_close(e);
+  if (e->barrier_scratch) cudaFree(e->barrier_scratch);
+  e->barrier_scratch = nullptr;
   if (e->comm && api().ok) api().CommDestroy((ncclComm_t)e->comm);
   e->comm = nullptr;
 }

@@ -545,6 +545,15 @@ int nbx_walk_width(nbx_engine* e, uint32_t* bodies_per_warp_step) {
   return NBX_OK;
 }
 
+int nbx_peer_export(nbx_engine* e, void* handle128) {
+  NBX_ENTER(e);
+  return peer_export(e, handle128);
+}
+int nbx_peer_import(nbx_engine* e, const void* handles) {
+  NBX_ENTER(e);
+  return peer_import(e, handles);
+}
+
 int nbx_comm_unique_id(void* id128) { return comm_unique_id(id128); }
 int nbx_comm_init_rank(nbx_engine* e, const void* id128) {
   NBX_ENTER(e);

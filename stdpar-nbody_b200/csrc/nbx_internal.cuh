@@ -104,6 +104,12 @@ struct nbx_engine {
 
   // NCCL (multi-GPU)
   void* comm = nullptr;
+  // peer-memory exchange of the BVH accelerations: the two local buffers `a` alternates between and, once imported, the
+  // other ranks' views of theirs (CUDA IPC), indexed [buffer][rank]
+  void* own_a[2]       = {nullptr, nullptr};
+  void* peer_a[2][16]  = {};
+  bool peers_ready     = false;
+  int* barrier_scratch = nullptr;
 
   // CUDA graph of one BVH time step (single GPU: the step has no host decision). The step flips the position buffer
   // and swaps v/a/ao with their alternates, so there is one graph per parity of `cur`.
@@ -206,6 +212,10 @@ int comm_init_rank(nbx_engine* e, const void* id128);
 int comm_allgather(nbx_engine* e, void* vec4_array);  // in place: rank r contributes records [r*chunk, (r+1)*chunk)
 int comm_allreduce_sum(nbx_engine* e, void* buffer, size_t count);  // in place, `count` elements of the engine's precision
 int comm_broadcast(nbx_engine* e, void* buffer, size_t bytes, int root);
+int comm_barrier(nbx_engine* e);  // every rank's earlier work on its stream is complete (and its peer stores visible) when this returns on the stream
+int peer_export(nbx_engine* e, void* handle128);
+int peer_import(nbx_engine* e, const void* handles);
+void peer_close(nbx_engine* e);
 // in place: rank q owns bytes [offset[q], offset[q] + count[q]) of `buffer`; afterwards every rank holds all of them
 int comm_allgatherv(nbx_engine* e, void* buffer, const size_t* offset, const size_t* count);
 void comm_destroy(nbx_engine* e);

@@ -23,6 +23,7 @@ FLAG_NO_FUSED_INTEGRATE = 0x2
 FLAG_ALLPAIRS_ORDERED = 0x4
 FLAG_ALLPAIRS_SYMMETRIC = 0x8
 UNIQUE_ID_BYTES = 128
+PEER_HANDLE_BYTES = 128
 PHASES = ("force", "accel", "bbox", "sort", "build", "multipoles", "traverse", "comm")
 
 # every symbol include/nbx.h declares (checked by tests/test_abi.py)
@@ -32,7 +33,7 @@ SYMBOLS = [
     "nbx_accelerate_step", "nbx_calc_energies", "nbx_bvh_bounding_box", "nbx_bvh_hilbert_sort", "nbx_bvh_build_tree",
     "nbx_bvh_compute_force", "nbx_bvh_get_keys", "nbx_bvh_get_nodes", "nbx_octree_build", "nbx_octree_compute_force",
     "nbx_octree_get_root", "nbx_octree_get_canonical", "nbx_stream_positions_begin", "nbx_stream_positions_end",
-    "nbx_comm_unique_id", "nbx_comm_init_rank",
+    "nbx_comm_unique_id", "nbx_comm_init_rank", "nbx_peer_export", "nbx_peer_import",
     "nbx_measure_fma_peak", "nbx_traversal_stats", "nbx_walk_width", "nbx_get_counters", "nbx_set_phase_timing", "nbx_get_phase_ms",
 ]
 
@@ -240,6 +241,19 @@ class Engine:
     def comm_init_rank(self, unique_id: bytes):
         assert len(unique_id) == UNIQUE_ID_BYTES
         _check(lib().nbx_comm_init_rank(self._h, C.c_char_p(unique_id)))
+
+    def peer_export(self) -> bytes:
+        buf = C.create_string_buffer(PEER_HANDLE_BYTES)
+        _check(lib().nbx_peer_export(self._h, buf))
+        return buf.raw
+
+    def peer_import(self, handles_in_rank_order):
+        """None: drop the peer buffers (back to the NCCL all-gather)."""
+        if handles_in_rank_order is None:
+            _check(lib().nbx_peer_import(self._h, None))
+            return
+        blob = b"".join(handles_in_rank_order)
+        _check(lib().nbx_peer_import(self._h, C.c_char_p(blob)))
 
     # ---- measurement --------------------------------------------------------------------------------------------
     def counters(self):
