@@ -435,14 +435,31 @@ struct PeerOut {
   int count;
 };
 
-template <typename T, int D, int NB, bool COUNT = false>
+// Small problems: pull the 32 B sector(s) of a left node's RIGHT SIBLING towards L1 together with the node's own load. Every
+// body that visits the left child visits the right one as soon as the left subtree is done, and at small n the walk is a
+// chain of dependent L2 round trips (about 300 cycles per step of the longest warp), not an issue-bound stream. Measured
+// (B200, step ms without / with): float n = 10 k 0.459 / 0.442, 30 k 0.910 / 0.806, 100 k 1.761 / 1.536, 200 k 2.256 / 2.188,
+// 400 k 3.93 / 4.02, 1 M 9.25 / 10.63; double 30 k 1.311 / 1.081, 100 k 2.481 / 2.089 — on below 250 k targets. Touching
+// the left child as well (the next node whenever a body opens) LOSES 3-20 % at every size, and so did `prefetch.global.L1`.
+// An ordinary load is used; ptxas deletes a load nobody reads (asm volatile or not), so the value is folded into a word
+// that is consumed one step later, when it has long landed.
+__device__ __forceinline__ unsigned touch_sector(const void* p) {
+  unsigned v;
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+template <typename T, int D, int NB, bool COUNT = false, bool TOUCH = false>
 __global__ void __launch_bounds__(128) bvh_force_key_kernel(const vec4_t<T>* __restrict__ xm, const WalkRec<T>* __restrict__ rec1,
                                                             uint32_t n, uint32_t tb, uint32_t te, uint32_t levels, T theta2, T c,
-                                                            vec4_t<T>* __restrict__ a_out, unsigned long long* stats, const PeerOut peers) {
+                                                            vec4_t<T>* __restrict__ a_out, unsigned long long* stats, const PeerOut peers,
+                                                            const uint32_t lanes) {
   // rec1 is the record array offset by -1 element: indexed by the 1-based heap index kk = k + 1
+  // lanes: bodies per warp and slot (32, or 16 / 8 for small problems: only the first `lanes` lanes carry bodies — the walk
+  // ends with its heaviest warp, and the union path of 8 neighbours is a third shorter than that of 32)
   constexpr bool PACK = sizeof(T) == 4 && NB % 2 == 0;  // FP32x2 over pairs of bodies
   const uint32_t lane  = threadIdx.x & 31u;
-  const uint32_t wbase = tb + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (32u * NB);  // first body of the warp
+  const uint32_t wbase = tb + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (lanes * NB);  // first body of the warp
   unsigned long long n_visit = 0, n_take = 0, n_step = 0;  // COUNT only
   // covered is even: covered >= n <=> covered >= n rounded up to even. Active keys are <= ((n_even - 2) << 4) + 27, so the
   // limit can sit 4 below n_even << 4: accepting the ROOT (a "right child" by parity of kk = 1) then needs no special case,
@@ -452,10 +469,11 @@ __global__ void __launch_bounds__(128) bvh_force_key_kernel(const vec4_t<T>* __r
   const uint32_t step0 = 16u << levels;  // key increment of accepting a level-0 node; >> level for deeper ones
   uint32_t idx[NB], key[NB];
   T px[NB], py[NB], pz[NB], ax[NB], ay[NB], az[NB];
+  unsigned t_pend = 0, t_sink = 0;  // TOUCH only
 #pragma unroll
   for (int j = 0; j < NB; ++j) {
-    idx[j]            = wbase + j * 32u + lane;
-    const bool valid  = idx[j] < te;
+    idx[j]            = wbase + j * lanes + lane;
+    const bool valid  = lane < lanes && idx[j] < te;
     const vec4_t<T> b = xm[valid ? idx[j] : tb];
     px[j] = b.x; py[j] = b.y; pz[j] = b.z;
     ax[j] = ay[j] = az[j] = T(0);
@@ -502,6 +520,13 @@ __global__ void __launch_bounds__(128) bvh_force_key_kernel(const vec4_t<T>* __r
     const WalkRec<T>* r = rec1 + kk;
     const vec4_t<T> nm  = *reinterpret_cast<const vec4_t<T>*>(r);  // (com, mass)
     const T w2          = r->w2;
+    if constexpr (TOUCH) {
+      t_sink ^= t_pend;  // last step's touch: landed long ago, no wait
+      if (!(kk & 1u)) {
+        t_pend = touch_sector(r + 1);
+        if (sizeof(T) == 8) t_pend ^= touch_sector(&r[1].w2);
+      }
+    }
     // accept: covered += 2^(levels-level); a right child (kk odd) continues one level up, a left child with its sibling
     const uint32_t cand_take = kmin + (step0 >> cl) - (kk & 1u);
     const uint32_t cand_open = kmin + 1u;
@@ -569,12 +594,14 @@ __global__ void __launch_bounds__(128) bvh_force_key_kernel(const vec4_t<T>* __r
   } else {
 #pragma unroll
     for (int j = 0; j < NB; ++j)
-      if (idx[j] < te) {
+      if (lane < lanes && idx[j] < te) {
         const vec4_t<T> r = make_v4<T>(mul_rn(c, ax[j]), mul_rn(c, ay[j]), D == 3 ? mul_rn(c, az[j]) : T(0), T(0));
         a_out[idx[j]] = r;
         for (int q = 0; q < peers.count; ++q) static_cast<vec4_t<T>*>(peers.p[q])[idx[j]] = r;
       }
     if (peers.count) __threadfence_system();
+    if constexpr (TOUCH)
+      if (t_sink == 0x7fc5a5a5u && n == 0u) a_out[0].x = T(0);  // never true (n > 0); keeps the touches alive
   }
 }
 
@@ -743,22 +770,46 @@ static int walk_bodies_per_lane(int prec, uint32_t targets) {
   return targets < 2500000u ? 1 : 2;
 }
 
+// bodies per warp and slot: small problems are bound by the LONGEST warp's chain of dependent steps (about 300 cycles
+// each), and the union path of fewer neighbours is shorter (tools/bvh_walk_sim.c, n = 100 k: max 7349 / 5908 / 4827 steps for
+// 32 / 16 / 8 bodies per warp) — while there are warp slots to spare, partially filled warps finish sooner. Measured (B200,
+// step ms for 32 / 16 / 8 bodies per warp, sibling touch on): float n = 10 k 0.442 / 0.435 / 0.360, 30 k 0.806 / 0.714 /
+// 0.688, 100 k 1.536 / 1.598 / 2.008; double 10 k 0.581 / 0.561 / 0.460, 30 k 1.081 / 0.967 / 0.952, 100 k 2.089 / 2.285 /
+// 2.991 (tools/exp_bvh_touch.py). A body's arithmetic does not depend on it: results are bit-identical (checked there).
+// NBX_BVH_LANES=8|16|32 forces it (experiments).
+static uint32_t walk_lanes(int nb, uint32_t targets) {
+  const char* v = getenv("NBX_BVH_LANES");
+  const int k   = v ? atoi(v) : 0;
+  if (k == 8 || k == 16 || k == 32) return uint32_t(k);
+  if (nb != 1) return 32u;
+  return targets <= 40000u ? 8u : (targets <= 70000u ? 16u : 32u);
+}
+// sibling sector touch (see touch_sector): on for the one-body-per-lane walk below 250 k targets; NBX_BVH_TOUCH=0|1 forces it
+static bool walk_touch(int nb, uint32_t targets) {
+  if (nb != 1) return false;
+  if (const char* v = getenv("NBX_BVH_TOUCH")) return atoi(v) != 0;
+  return targets <= 250000u;
+}
+
 template <typename T, int D, bool COUNT>
 static int launch_walk(nbx_engine* e, BvhState<T>* s, unsigned long long* stats) {
   const uint32_t nt = e->te - e->tb;
   const T theta     = T(e->cfg.theta);
   const int nb      = walk_bodies_per_lane(e->prec, nt);
+  const uint32_t lanes = walk_lanes(nb, nt);
   const auto* xm    = static_cast<const vec4_t<T>*>(e->xm[e->cur]);
   auto* a           = static_cast<vec4_t<T>*>(e->a);
-  const unsigned grid = (nt + 128u * nb - 1) / (128u * nb);
+  const unsigned grid = (nt + 4u * lanes * nb - 1) / (4u * lanes * nb);
   PeerOut peers{};
   if (!COUNT && e->peers_ready && e->cfg.world_size > 1) {
     const int k = e->a == e->own_a[0] ? 0 : 1;  // which of its two buffers `a` is right now (the same on every rank)
     for (int r = 0; r < e->cfg.world_size; ++r)
       if (r != e->cfg.rank) peers.p[peers.count++] = e->peer_a[k][r];
   }
-#define NBX_WALK(NB_) bvh_force_key_kernel<T, D, NB_, COUNT><<<grid, 128, 0, e->stream>>>(xm, s->rec - 1, e->n, e->tb, e->te, s->levels, theta * theta, T(e->cfg.G), a, stats, peers)
-  if (nb == 1) NBX_WALK(1);
+#define NBX_WALK(NB_) bvh_force_key_kernel<T, D, NB_, COUNT><<<grid, 128, 0, e->stream>>>(xm, s->rec - 1, e->n, e->tb, e->te, s->levels, theta * theta, T(e->cfg.G), a, stats, peers, lanes)
+  if (nb == 1 && walk_touch(nb, nt))
+    bvh_force_key_kernel<T, D, 1, COUNT, true><<<grid, 128, 0, e->stream>>>(xm, s->rec - 1, e->n, e->tb, e->te, s->levels, theta * theta, T(e->cfg.G), a, stats, peers, lanes);
+  else if (nb == 1) NBX_WALK(1);
   else if (nb == 2) NBX_WALK(2);
   else NBX_WALK(4);
 #undef NBX_WALK
@@ -890,7 +941,10 @@ void bvh_after_graph_replay(nbx_engine* e) {
   std::swap(e->a, e->a_alt);
   std::swap(e->ao, e->ao_alt);
 }
-int bvh_walk_width(const nbx_engine* e) { return 32 * walk_bodies_per_lane(e->prec, e->te - e->tb); }
+int bvh_walk_width(const nbx_engine* e) {
+  const int nb = walk_bodies_per_lane(e->prec, e->te - e->tb);
+  return int(walk_lanes(nb, e->te - e->tb)) * nb;
+}
 int bvh_get_bbox(nbx_engine* e, void* xmin, void* xmax) { return BVH_DISPATCH(e, get_bbox_impl, e, xmin, xmax); }
 int bvh_get_keys(nbx_engine* e, uint64_t* keys, uint32_t* perm) { return BVH_DISPATCH(e, get_keys_impl, e, keys, perm); }
 int bvh_get_nodes(nbx_engine* e, uint64_t* nnodes, void* node_m, void* bw, void* b) {

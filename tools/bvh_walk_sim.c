@@ -28,6 +28,11 @@ static inline int accept(const float* xs, const float* nm, float w2, float th2) 
   return w2 < th2 * d2;
 }
 
+static int cmp_u32(const void* a, const void* b) {
+  uint32_t x = *(const uint32_t*)a, y = *(const uint32_t*)b;
+  return x < y ? -1 : x > y;
+}
+
 int main(int argc, char** argv) {
   uint32_t n      = argc > 1 ? (uint32_t)atol(argv[1]) : 1000000;
   uint32_t stride = argc > 2 ? (uint32_t)atol(argv[2]) : 16;
@@ -54,6 +59,8 @@ int main(int argc, char** argv) {
   uint64_t A_steps = 0, A_act = 0, A_anytake = 0, A_body = 0, A_left = 0, A_left_alltake = 0;
   uint64_t B_steps = 0, B_tests = 0, B_rpart = 0, B_body = 0, B_any_take = 0, B_testsL = 0, B_testsR = 0;
   uint64_t warps = 0;
+  const int64_t nwarps_all = (int64_t)((n + LANES - 1) / LANES);
+  uint32_t* per_warp = calloc((size_t)nwarps_all, 4); /* A's steps of every sampled warp: the walk ends with the heaviest one */
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : A_steps, A_act, A_anytake, A_body, A_left, A_left_alltake, B_steps, B_tests, B_rpart, B_body, B_any_take, B_testsL, B_testsR, warps)
   for (int64_t w = 0; w < (int64_t)((n + LANES - 1) / LANES); w += stride) {
     ++warps;
@@ -66,6 +73,7 @@ int main(int argc, char** argv) {
       for (int l = 0; l < LANES; ++l) kmin = key[l] < kmin ? key[l] : kmin;
       if (kmin >= nlim) break;
       ++A_steps;
+      ++per_warp[w];
       const uint32_t cl = kmin & 31u;
       if (cl == levels) {
         ++A_body;
@@ -131,6 +139,14 @@ int main(int argc, char** argv) {
   printf("A: steps/warp=%.0f  tests/body=%.0f  lane util=%.3f  body-level steps=%.3f  steps with any take=%.3f  left-node steps=%.3f of which all active lanes take=%.3f\n",
          (double)A_steps / warps, (double)A_act / (warps * (double)LANES), (double)A_act / ((double)LANES * A_steps), (double)A_body / A_steps,
          (double)A_anytake / A_steps, (double)A_left / A_steps, (double)A_left_alltake / (A_left ? A_left : 1));
+  {
+    uint32_t* q = malloc((size_t)warps * 4);
+    size_t c = 0;
+    for (int64_t w = 0; w < nwarps_all; w += stride) q[c++] = per_warp[w];
+    qsort(q, c, 4, cmp_u32);
+    printf("A: steps per warp: median %u  p90 %u  p99 %u  max %u  (max / mean = %.2f)\n", q[c / 2], q[c * 9 / 10], q[c * 99 / 100], q[c - 1],
+           q[c - 1] / ((double)A_steps / warps));
+  }
   printf("B: steps/warp=%.0f (%.3f of A)  tests/body=%.0f (L %.0f R %.0f)  steps needing the R half=%.3f  body-level=%.3f any take=%.3f\n",
          (double)B_steps / warps, (double)B_steps / A_steps, (double)B_tests / (warps * (double)LANES), (double)B_testsL / (warps * (double)LANES),
          (double)B_testsR / (warps * (double)LANES), (double)B_rpart / B_steps, (double)B_body / B_steps, (double)B_any_take / B_steps);
