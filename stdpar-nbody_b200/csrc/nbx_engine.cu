@@ -541,7 +541,7 @@ int nbx_traversal_stats(nbx_engine* e, uint64_t* node_visits, uint64_t* interact
 int nbx_walk_width(nbx_engine* e, uint32_t* bodies_per_warp_step) {
   if (!e || !bodies_per_warp_step) return fail(NBX_ERR_INVALID, "NULL argument");
   if (e->algo != NBX_BVH && e->algo != NBX_OCTREE) return fail(NBX_ERR_STATE, "walk width needs a tree engine");
-  *bodies_per_warp_step = e->algo == NBX_BVH ? uint32_t(bvh_walk_width(e)) : 32u;
+  *bodies_per_warp_step = e->algo == NBX_BVH ? uint32_t(bvh_walk_width(e)) : (e->algo == NBX_OCTREE ? uint32_t(octree_walk_width(e)) : 32u);
   return NBX_OK;
 }
 

@@ -499,13 +499,14 @@ __global__ void __launch_bounds__(128) octree_force_kernel(const vec4_t<T>* __re
                                                            const Root<T>* __restrict__ root, const uint32_t* __restrict__ cell_base,
                                                            const uint32_t* __restrict__ order, uint32_t n, uint32_t tb, uint32_t te,
                                                            const T* __restrict__ s_table, T c, vec4_t<T>* __restrict__ a_sorted,
-                                                           unsigned long long* stats = nullptr) {
+                                                           unsigned long long* stats, const uint32_t lanes) {
   __shared__ T tab[132];
   for (uint32_t d = threadIdx.x; d < 132; d += blockDim.x) tab[d] = s_table[d];
   __syncthreads();
   unsigned long long n_visit = 0, n_take = 0, n_step = 0;  // COUNT only
-  const uint32_t t    = tb + blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid    = t < te;
+  // lanes: bodies per warp (32, or 16 / 8 for small problems: only the first `lanes` lanes carry bodies, see oct_walk_lanes)
+  const uint32_t t    = tb + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * lanes + (threadIdx.x & 31u);
+  const bool valid    = (threadIdx.x & 31u) < lanes && t < te;
   const uint32_t nrec = n + root->cells;
   const uint32_t tt   = order ? order[valid ? t : tb] : (valid ? t : tb);  // sorted slot of this lane's body
   const vec4_t<T> xs  = mono[tt + cell_base[tt + 1]];  // own leaf record = own position
@@ -616,13 +617,14 @@ __global__ void __launch_bounds__(128) octree_force_thr_kernel(const vec4_t<T>* 
                                                                const Root<T>* __restrict__ root, const uint32_t* __restrict__ cell_base,
                                                                const uint32_t* __restrict__ order, uint32_t n, uint32_t tb, uint32_t te,
                                                                const T* __restrict__ thr_table, T c, vec4_t<T>* __restrict__ a_sorted,
-                                                               unsigned long long* stats = nullptr) {
+                                                               unsigned long long* stats, const uint32_t lanes) {
   __shared__ T tab[132];  // tau(depth) ; [128] = 0, leaf: always accepted
   for (uint32_t d = threadIdx.x; d < 132; d += blockDim.x) tab[d] = thr_table[d];
   __syncthreads();
   unsigned long long n_visit = 0, n_take = 0, n_step = 0;  // COUNT only
-  const uint32_t t    = tb + blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid    = t < te;
+  // lanes: bodies per warp (32, or 16 / 8 for small problems: only the first `lanes` lanes carry bodies, see oct_walk_lanes)
+  const uint32_t t    = tb + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * lanes + (threadIdx.x & 31u);
+  const bool valid    = (threadIdx.x & 31u) < lanes && t < te;
   const uint32_t nrec = n + root->cells;
   const uint32_t tt   = order ? order[valid ? t : tb] : (valid ? t : tb);  // sorted slot of this lane's body
   const vec4_t<T> xs  = mono[tt + cell_base[tt + 1]];  // own leaf record = own position
@@ -872,6 +874,35 @@ static int check_overflow(nbx_engine* e) {
   return NBX_OK;
 }
 
+// bodies per warp of the walks: at small n the walk ends with its longest warp's chain of dependent steps, and the union
+// path of fewer neighbours is shorter (as for the BVH, nbx_bvh.cu walk_lanes). The octree gains less — its build is half of
+// a small step. Measured (B200, step ms for 32 / 16 / 8 bodies per warp, tools/exp_oct_small.py): double n = 10 k 0.499 /
+// 0.470 / 0.447, 30 k 0.659 / 0.645 / 0.629, 100 k 0.968 / 0.948 / 1.146; float 10 k 0.381 / 0.373 / 0.369, 30 k 0.441 /
+// 0.437 / 0.443, 100 k 0.667 / 0.684 / 0.815. Results are bit-identical (checked there). Look-ahead sector touches of the
+// records 1, 2 or 4 steps on (the walk mostly moves to p + 1) were measured with it: no gain at 10 k - 30 k, 5 - 25 % slower
+// from 100 k; not kept. NBX_OCT_LANES=8|16|32 forces the width (experiments).
+static uint32_t oct_walk_lanes(uint32_t targets) {
+  const char* v = getenv("NBX_OCT_LANES");
+  const int k   = v ? atoi(v) : 0;
+  if (k == 8 || k == 16 || k == 32) return uint32_t(k);
+  return targets <= 20000u ? 8u : (targets <= 40000u ? 16u : 32u);
+}
+int octree_walk_width(const nbx_engine* e) { return int(oct_walk_lanes(e->te - e->tb)); }
+
+template <typename T, int D, bool COUNT>
+static void launch_oct_walk(nbx_engine* e, OctreeState<T>* s, int walk, unsigned long long* stats) {
+  const uint32_t nt    = e->te - e->tb;
+  const uint32_t lanes = oct_walk_lanes(nt);
+  const unsigned grid  = (nt + 4u * lanes - 1) / (4u * lanes);
+  const uint32_t* ord  = s->hilbert_targets ? s->order : nullptr;
+  if (walk == 2)
+    octree_force_thr_kernel<T, D, COUNT><<<grid, 128, 0, e->stream>>>(s->mono, s->meta, s->root, s->cnt, ord, e->n, e->tb, e->te, s->thr_table,
+                                                                      T(e->cfg.G), s->a_sorted, stats, lanes);
+  else
+    octree_force_kernel<T, D, COUNT><<<grid, 128, 0, e->stream>>>(s->mono, s->meta, s->root, s->cnt, ord, e->n, e->tb, e->te, s->thr_table,
+                                                                  T(e->cfg.G), s->a_sorted, stats, lanes);
+}
+
 template <typename T, int D>
 static int force_impl(nbx_engine* e) {
   auto* s = st<T>(e);
@@ -884,12 +915,7 @@ static int force_impl(nbx_engine* e) {
     static const int forced = [] { const char* v = getenv("NBX_OCT_WALK"); return v ? atoi(v) : 0; }();
     const int walk = forced ? forced : (sizeof(T) == 8 ? 2 : 1);
     threshold_table_kernel<T><<<1, 160, 0, e->stream>>>(s->root, T(e->cfg.theta), s->thr_table);
-    if (walk == 2)
-      octree_force_thr_kernel<T, D><<<(nt + 127) / 128, 128, 0, e->stream>>>(s->mono, s->meta, s->root, s->cnt, s->hilbert_targets ? s->order : nullptr, e->n, e->tb, e->te,
-                                                                            s->thr_table, T(e->cfg.G), s->a_sorted);
-    else
-      octree_force_kernel<T, D><<<(nt + 127) / 128, 128, 0, e->stream>>>(s->mono, s->meta, s->root, s->cnt, s->hilbert_targets ? s->order : nullptr, e->n, e->tb, e->te,
-                                                                        s->thr_table, T(e->cfg.G), s->a_sorted);
+    launch_oct_walk<T, D, false>(e, s, walk, nullptr);
     e->launches += 2;
   }
   if (e->cfg.world_size > 1) NBX_TRY(comm_allgather(e, s->a_sorted));
@@ -952,12 +978,7 @@ static int stats_impl(nbx_engine* e, unsigned long long* dev_stats) {
   const uint32_t nt = e->te - e->tb;
   if (nt) {  // the counting twin of the walk force_impl launches
     threshold_table_kernel<T><<<1, 160, 0, e->stream>>>(s->root, T(e->cfg.theta), s->thr_table);
-    if (sizeof(T) == 8)
-      octree_force_thr_kernel<T, D, true><<<(nt + 127) / 128, 128, 0, e->stream>>>(s->mono, s->meta, s->root, s->cnt, s->hilbert_targets ? s->order : nullptr, e->n, e->tb, e->te,
-                                                                                  s->thr_table, T(e->cfg.G), s->a_sorted, dev_stats);
-    else
-      octree_force_kernel<T, D, true><<<(nt + 127) / 128, 128, 0, e->stream>>>(s->mono, s->meta, s->root, s->cnt, s->hilbert_targets ? s->order : nullptr, e->n, e->tb, e->te,
-                                                                              s->thr_table, T(e->cfg.G), s->a_sorted, dev_stats);
+    launch_oct_walk<T, D, true>(e, s, sizeof(T) == 8 ? 2 : 1, dev_stats);
     e->launches += 2;
   }
   NBX_CUDA(cudaGetLastError());
