@@ -156,3 +156,26 @@ def test_degenerate_geometries_bvh_and_octree(oracle, oracle_fast, dt, dim):
         assert same(gd, depth) and same(gk, kind) and same(gmo, mo), name
         ref, _ = oracle_fast.octree_force(s["x"], t, s["G"], 0.5)
         assert rms(rel_err(a, ref)) <= (5e-5 if dt == np.float32 else 1e-12), name
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("algo", ["bvh", "octree"])
+def test_small_n_walk_variants_keep_every_bit(oracle, monkeypatch, algo, dt):
+    """Small problems run the tree walks with partially filled warps (8 / 16 bodies per warp) and, for the BVH, a sector
+    touch of the right sibling. Neither changes a body's sequence of tests or its arithmetic: the whole
+    state after three steps is the same bit for bit for every combination (NBX_BVH_LANES / NBX_OCT_LANES / NBX_BVH_TOUCH)."""
+    n, dim = 6000, 3
+    s = oracle.galaxy(n, dt, dim)
+    got = []
+    for lanes in ("32", "16", "8"):
+        for touch in ("0", "1"):
+            monkeypatch.setenv("NBX_BVH_LANES", lanes)
+            monkeypatch.setenv("NBX_OCT_LANES", lanes)
+            monkeypatch.setenv("NBX_BVH_TOUCH", touch)
+            with nbx.Engine(n, dim, dt, algo, s["dt"], s["G"], theta=0.5) as e:
+                e.upload_state(s)
+                e.step(3)
+                got.append(e.download())
+    for other in got[1:]:
+        for k in ("m", "x", "v", "a", "ao"):
+            assert other[k].tobytes() == got[0][k].tobytes(), k
