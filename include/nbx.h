@@ -171,11 +171,12 @@ int nbx_peer_import(nbx_engine* e, const void* handles_world_x_128);
 int nbx_measure_fma_peak(int device, int precision, double* tflops);
 /* Tree engines: re-runs the traversal of the LAST built tree in counting mode (no state is modified) and returns, for
  * this rank's targets, the number of (body, node) tests, of accepted interactions (body-level pairs count as one), and
- * of warp-level steps (= records loaded per warp). Used for the HBM/L2 roofline of the walk: algorithmic bytes =
- * node_visits x node record size. */
+ * of warp-level steps (= records loaded per warp). Used for the issue-rate roofline of the walk (instructions per warp
+ * step x warp_steps / walk time, bench.py) and for the parity check that the device performs exactly the oracle's tests. */
 int nbx_traversal_stats(nbx_engine* e, uint64_t* node_visits, uint64_t* interactions, uint64_t* warp_steps);
-/* bodies a warp of the tree walk serves per step (octree: 32, one per lane; bvh: 32 x bodies per lane): the denominator
- * of the lane utilisation node_visits / (warp_steps x width). */
+/* bodies a warp of the tree walk serves per step: lanes carrying bodies (32; 16 or 8 for small problems, whose walks end
+ * with their longest warp) x bodies per lane (octree: 1; bvh: 1, 2 or 4). The denominator of the lane utilisation
+ * node_visits / (warp_steps x width). */
 int nbx_walk_width(nbx_engine* e, uint32_t* bodies_per_warp_step);
 /* counters of the engine since creation: kernels launched by this library, bytes copied H2D / D2H */
 int nbx_get_counters(nbx_engine* e, uint64_t* kernel_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes);

@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(128) bvh_force_kernel(const vec4_t<T>* __restr
 // for every body (the node loads are warp-uniform anyway); only the accumulation is predicated. A body is finished when
 // covered >= n, i.e. key >= nlim; the warp stops when the minimum is.
 //
-// NB bodies per lane (32*NB consecutive Hilbert-sorted bodies per warp): the bookkeeping of a step — REDUX, node index,
+// NB bodies per lane (32*NB consecutive Hilbert-sorted bodies per warp; fewer lanes carry bodies at small n, see walk_lanes): the bookkeeping of a step — REDUX, node index,
 // address, record load, candidates, loop control, about two thirds of the instructions — is shared by NB tests, and the
 // union of 64 (128) neighbouring paths is only 1.12x (1.30x) longer than that of 32 (tools/bvh_walk_sim.c, n = 10 M:
 // 10257 / 11499 / 13339 steps per warp for NB = 1 / 2 / 4). In float the NB tests run two at a time on FP32x2

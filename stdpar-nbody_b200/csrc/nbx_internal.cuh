@@ -193,7 +193,7 @@ int bvh_compute_force(nbx_engine* e);
 int bvh_get_bbox(nbx_engine* e, void* xmin, void* xmax);
 void bvh_after_graph_replay(nbx_engine* e);                      // host-side effects of a replayed step (buffer swaps)
 int octree_walk_width(const nbx_engine* e);                     // bodies per warp step of the octree walk (32, 16 or 8)
-int bvh_walk_width(const nbx_engine* e);                        // bodies per warp step of the walk (32 x bodies per lane)
+int bvh_walk_width(const nbx_engine* e);                        // bodies per warp step of the walk (lanes carrying bodies x bodies per lane)
 int bvh_stats(nbx_engine* e, unsigned long long* dev_stats);     // counting variant of the walk: {visits, interactions, warp steps}
 int bvh_get_keys(nbx_engine* e, uint64_t* keys, uint32_t* perm);
 int bvh_get_nodes(nbx_engine* e, uint64_t* nnodes, void* node_m, void* bw, void* b);
